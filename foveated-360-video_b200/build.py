@@ -1,0 +1,81 @@
+#!/usr/bin/env python3
+"""In-tree nvcc build of libfov360.so (sm_100a only).
+
+The shared library lands next to this file so that it travels to the GPU box with the
+repository snapshot.  No JIT, no torch extension machinery: plain ``nvcc`` per translation
+unit (run in parallel), then one link step.  ``luts.cc`` holds the host-side table builders
+and is compiled with ``-ffp-contract=off`` because its truncating float formulas must round
+every operation separately (see the header of that file).
+"""
+from __future__ import annotations
+
+import concurrent.futures as cf
+import os
+import shutil
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+CSRC = os.path.join(HERE, "csrc")
+INCLUDE = os.path.join(ROOT, "include")
+OBJ_DIR = os.path.join(HERE, "build")
+LIB_PATH = os.path.join(HERE, "libfov360.so")
+
+SOURCES = ["capi.cu", "sat_encode.cu", "sat_decode.cu", "image_sampler.cu", "luts.cc"]
+HEADERS = [os.path.join(CSRC, "fov360_internal.h"), os.path.join(INCLUDE, "fov360.h")]
+
+ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
+NVCC_FLAGS = [
+    "-O3", "-std=c++17", "-lineinfo", *ARCH,
+    "-Xcompiler", "-fPIC,-ffp-contract=off,-fno-fast-math",
+    "-I", INCLUDE, "-I", CSRC,
+]
+
+
+def nvcc_path() -> str:
+    for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and os.path.exists(cand):
+            return cand
+    raise RuntimeError("nvcc not found: libfov360.so cannot be built (there is no CPU fallback)")
+
+
+def _stale(target: str, deps: list[str]) -> bool:
+    if not os.path.exists(target):
+        return True
+    t = os.path.getmtime(target)
+    return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
+
+
+def _compile(nvcc: str, src: str, obj: str, verbose: bool) -> None:
+    cmd = [nvcc, *NVCC_FLAGS, "-c", src, "-o", obj]
+    if verbose:
+        cmd.insert(1, "-Xptxas=-v")
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if verbose or r.returncode:
+        sys.stderr.write(r.stdout + r.stderr)
+    if r.returncode:
+        raise RuntimeError("nvcc failed for " + src)
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    """Builds (if stale) and returns the path of libfov360.so."""
+    srcs = [os.path.join(CSRC, s) for s in SOURCES]
+    if not force and not _stale(LIB_PATH, srcs + HEADERS + [os.path.abspath(__file__)]):
+        return LIB_PATH
+    nvcc = nvcc_path()
+    os.makedirs(OBJ_DIR, exist_ok=True)
+    objs = [os.path.join(OBJ_DIR, os.path.splitext(s)[0] + ".o") for s in SOURCES]
+    todo = [(s, o) for s, o in zip(srcs, objs)
+            if force or _stale(o, [s] + HEADERS + [os.path.abspath(__file__)])]
+    with cf.ThreadPoolExecutor(max_workers=max(1, min(len(todo), os.cpu_count() or 1))) as ex:
+        for fut in [ex.submit(_compile, nvcc, s, o, verbose) for s, o in todo]:
+            fut.result()
+    tmp = LIB_PATH + ".tmp"
+    subprocess.check_call([nvcc, *ARCH, "-shared", "-cudart", "static", "-o", tmp, *objs])
+    os.replace(tmp, LIB_PATH)
+    return LIB_PATH
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

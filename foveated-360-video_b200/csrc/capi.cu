@@ -1,0 +1,659 @@
+// C ABI of libfov360.so (see include/fov360.h): context / memory management, table caches and
+// argument validation in front of the kernel launchers.  There is no CPU fallback anywhere in
+// this file: without a CUDA device fov_ctx_create() fails and nothing else can be called.
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+
+#include "fov360_internal.h"
+
+using namespace fov;
+
+struct fov_ctx {
+  int device = 0;
+  int sm_count = 148;
+  cudaStream_t stream = nullptr;
+  std::string last_error;
+  uint64_t launches = 0;
+  Profiler prof;
+  LaunchCtx lc() { return LaunchCtx{stream, sm_count, &prof, &launches}; }
+  SatScratch sat_scratch;
+  std::map<std::tuple<int, int, int, int>, SatGrid> sat_grids;
+  std::map<std::tuple<int, int, int, int>, InterpLut> interp_luts;
+  std::map<std::tuple<int, int, int, int>, ImgGrid> img_grids;
+  std::map<std::tuple<int, int>, LogpolarGrid> lp_grids;
+  // The reference objects hold ONE current grid; lazily-initialised samplers use it.
+  const SatGrid *cur_sat_grid = nullptr;
+};
+
+namespace fov {
+
+cudaEvent_t Profiler::get() {
+  if (!pool.empty()) {
+    cudaEvent_t e = pool.back();
+    pool.pop_back();
+    return e;
+  }
+  cudaEvent_t e = nullptr;
+  cudaEventCreate(&e);
+  return e;
+}
+
+void Profiler::collect() {
+  for (const Pending &p : pending) {
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, p.a, p.b) == cudaSuccess) {
+      Total &t = totals[p.name];
+      t.ms += ms;
+      t.launches += 1;
+    }
+    pool.push_back(p.a);
+    pool.push_back(p.b);
+  }
+  pending.clear();
+}
+
+void Profiler::release() {
+  collect();
+  for (cudaEvent_t e : pool) cudaEventDestroy(e);
+  pool.clear();
+}
+
+}  // namespace fov
+
+namespace {
+
+std::string g_global_error;
+
+int fail(fov_ctx *ctx, int code, const std::string &msg) {
+  if (ctx)
+    ctx->last_error = msg;
+  else
+    g_global_error = msg;
+  return code;
+}
+
+int cuda_fail(fov_ctx *ctx, cudaError_t e, const char *what) {
+  return fail(ctx, (int)e, std::string(what) + ": " + cudaGetErrorName(e) + " (" +
+                               cudaGetErrorString(e) + ")");
+}
+
+#define FOV_REQUIRE_CTX(ctx) \
+  if (!(ctx)) return fail(nullptr, FOV_ERR_NO_CONTEXT, "fov360: not initialized with a CUDA context")
+#define FOV_CUDA(ctx, expr, what)                        \
+  do {                                                   \
+    cudaError_t e_ = (expr);                             \
+    if (e_ != cudaSuccess) return cuda_fail(ctx, e_, what); \
+  } while (0)
+
+struct DeviceGuard {
+  explicit DeviceGuard(const fov_ctx *c) { cudaSetDevice(c->device); }
+};
+
+template <class T>
+cudaError_t upload(fov_ctx *ctx, T **dptr, const std::vector<T> &h) {
+  cudaError_t e = cudaMalloc(reinterpret_cast<void **>(dptr), h.size() * sizeof(T));
+  if (e != cudaSuccess) return e;
+  // Table uploads are init-time; a blocking copy keeps the host vectors' lifetime trivial.
+  e = cudaMemcpyAsync(*dptr, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice, ctx->stream);
+  if (e != cudaSuccess) return e;
+  return cudaStreamSynchronize(ctx->stream);
+}
+
+bool dims_ok(int ow, int oh, int W, int H) {
+  // int16 tables (like the reference's grid) hold deltas up to ~1.01*dim.
+  return ow > 0 && oh > 0 && W > 0 && H > 0 && W <= 30000 && H <= 30000 && ow <= 30000 &&
+         oh <= 30000;
+}
+
+int get_sat_grid(fov_ctx *ctx, int ow, int oh, int W, int H, const SatGrid **out) {
+  if (!dims_ok(ow, oh, W, H)) return fail(ctx, FOV_ERR_INVALID, "sat grid: invalid dimensions");
+  auto key = std::make_tuple(ow, oh, W, H);
+  auto it = ctx->sat_grids.find(key);
+  if (it == ctx->sat_grids.end()) {
+    SatGrid g;
+    g.ow = ow, g.oh = oh, g.W = W, g.H = H;
+    build_sat_grid_edges(ow, oh, W, H, g.h_xedge, g.h_yedge);
+    FOV_CUDA(ctx, upload(ctx, &g.d_xedge, g.h_xedge), "sat grid upload");
+    FOV_CUDA(ctx, upload(ctx, &g.d_yedge, g.h_yedge), "sat grid upload");
+    it = ctx->sat_grids.emplace(key, std::move(g)).first;
+  }
+  *out = &it->second;
+  return FOV_OK;
+}
+
+int get_interp_lut(fov_ctx *ctx, int W, int H, int ow, int oh, const InterpLut **out) {
+  if (!dims_ok(ow, oh, W, H)) return fail(ctx, FOV_ERR_INVALID, "interp lut: invalid dimensions");
+  auto key = std::make_tuple(W, H, ow, oh);
+  auto it = ctx->interp_luts.find(key);
+  if (it == ctx->interp_luts.end()) {
+    InterpLut l;
+    l.W = W, l.H = H, l.ow = ow, l.oh = oh;
+    std::vector<InterpEntry> hx, hy;
+    build_interp_axis(W, ow, hx);
+    build_interp_axis(H, oh, hy);
+    FOV_CUDA(ctx, upload(ctx, &l.d_x, hx), "interp lut upload");
+    FOV_CUDA(ctx, upload(ctx, &l.d_y, hy), "interp lut upload");
+    it = ctx->interp_luts.emplace(key, l).first;
+  }
+  *out = &it->second;
+  return FOV_OK;
+}
+
+int get_img_grid(fov_ctx *ctx, int ow, int oh, int W, int H, const ImgGrid **out) {
+  if (!dims_ok(ow, oh, W, H)) return fail(ctx, FOV_ERR_INVALID, "img grid: invalid dimensions");
+  auto key = std::make_tuple(ow, oh, W, H);
+  auto it = ctx->img_grids.find(key);
+  if (it == ctx->img_grids.end()) {
+    ImgGrid g;
+    g.ow = ow, g.oh = oh, g.W = W, g.H = H;
+    build_img_grid_axes(ow, oh, W, H, g.h_xd, g.h_yd);
+    FOV_CUDA(ctx, upload(ctx, &g.d_xd, g.h_xd), "img grid upload");
+    FOV_CUDA(ctx, upload(ctx, &g.d_yd, g.h_yd), "img grid upload");
+    it = ctx->img_grids.emplace(key, std::move(g)).first;
+  }
+  *out = &it->second;
+  return FOV_OK;
+}
+
+int get_lp_grid(fov_ctx *ctx, int ow, int oh, const LogpolarGrid **out) {
+  if (!dims_ok(ow, oh, 1, 1)) return fail(ctx, FOV_ERR_INVALID, "logpolar grid: invalid dimensions");
+  auto key = std::make_tuple(ow, oh);
+  auto it = ctx->lp_grids.find(key);
+  if (it == ctx->lp_grids.end()) {
+    LogpolarGrid g;
+    g.ow = ow, g.oh = oh;
+    build_logpolar_axes(ow, oh, g.h_radius, g.h_cos, g.h_sin);
+    FOV_CUDA(ctx, upload(ctx, &g.d_radius, g.h_radius), "logpolar grid upload");
+    FOV_CUDA(ctx, upload(ctx, &g.d_cos, g.h_cos), "logpolar grid upload");
+    FOV_CUDA(ctx, upload(ctx, &g.d_sin, g.h_sin), "logpolar grid upload");
+    it = ctx->lp_grids.emplace(key, std::move(g)).first;
+  }
+  *out = &it->second;
+  return FOV_OK;
+}
+
+int ensure_sat_scratch(fov_ctx *ctx, int n, int W, int H) {
+  const size_t need = sat_scratch_bytes(n, W, H);
+  if (need <= ctx->sat_scratch.bytes) return FOV_OK;
+  if (ctx->sat_scratch.base) {
+    FOV_CUDA(ctx, cudaStreamSynchronize(ctx->stream), "sat scratch resize");
+    FOV_CUDA(ctx, cudaFree(ctx->sat_scratch.base), "sat scratch free");
+    ctx->sat_scratch = SatScratch();
+  }
+  FOV_CUDA(ctx, cudaMalloc(&ctx->sat_scratch.base, need), "sat scratch alloc");
+  ctx->sat_scratch.bytes = need;
+  return FOV_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int fov_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+  return n;
+}
+
+fov_ctx *fov_ctx_create(int device, int *err) {
+  auto set = [&](int code, const std::string &m) {
+    g_global_error = m;
+    if (err) *err = code;
+    return (fov_ctx *)nullptr;
+  };
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0)
+    return set(FOV_ERR_NO_DEVICE,
+               std::string("fov360: no usable CUDA device (there is no CPU fallback): ") +
+                   (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0"));
+  if (device < 0 || device >= n) return set(FOV_ERR_INVALID, "fov360: device index out of range");
+  e = cudaSetDevice(device);
+  if (e != cudaSuccess) return set((int)e, std::string("cudaSetDevice: ") + cudaGetErrorString(e));
+  std::unique_ptr<fov_ctx> ctx(new fov_ctx);
+  ctx->device = device;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
+  e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+  if (e != cudaSuccess)
+    return set((int)e, std::string("cudaStreamCreate: ") + cudaGetErrorString(e));
+  if (err) *err = FOV_OK;
+  return ctx.release();
+}
+
+void fov_ctx_destroy(fov_ctx *ctx) {
+  if (!ctx) return;
+  DeviceGuard g(ctx);
+  cudaStreamSynchronize(ctx->stream);
+  for (auto &kv : ctx->sat_grids) {
+    cudaFree(kv.second.d_xedge);
+    cudaFree(kv.second.d_yedge);
+  }
+  for (auto &kv : ctx->interp_luts) {
+    cudaFree(kv.second.d_x);
+    cudaFree(kv.second.d_y);
+  }
+  for (auto &kv : ctx->img_grids) {
+    cudaFree(kv.second.d_xd);
+    cudaFree(kv.second.d_yd);
+  }
+  for (auto &kv : ctx->lp_grids) {
+    cudaFree(kv.second.d_radius);
+    cudaFree(kv.second.d_cos);
+    cudaFree(kv.second.d_sin);
+  }
+  if (ctx->sat_scratch.base) cudaFree(ctx->sat_scratch.base);
+  ctx->prof.release();
+  cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+const char *fov_last_error_string(const fov_ctx *ctx) {
+  return ctx ? ctx->last_error.c_str() : g_global_error.c_str();
+}
+
+int fov_ctx_device(const fov_ctx *ctx) { return ctx ? ctx->device : -1; }
+void *fov_ctx_stream(const fov_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
+uint64_t fov_ctx_launch_count(const fov_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+int fov_sync(fov_ctx *ctx) {
+  FOV_REQUIRE_CTX(ctx);
+  DeviceGuard g(ctx);
+  FOV_CUDA(ctx, cudaStreamSynchronize(ctx->stream), "fov_sync");
+  return FOV_OK;
+}
+
+int fov_profile_enable(fov_ctx *ctx, int on) {
+  FOV_REQUIRE_CTX(ctx);
+  DeviceGuard g(ctx);
+  FOV_CUDA(ctx, cudaStreamSynchronize(ctx->stream), "fov_profile_enable");
+  ctx->prof.collect();
+  ctx->prof.enabled = on != 0;
+  return FOV_OK;
+}
+
+int fov_profile_reset(fov_ctx *ctx) {
+  FOV_REQUIRE_CTX(ctx);
+  DeviceGuard g(ctx);
+  FOV_CUDA(ctx, cudaStreamSynchronize(ctx->stream), "fov_profile_reset");
+  ctx->prof.collect();
+  ctx->prof.totals.clear();
+  return FOV_OK;
+}
+
+int fov_profile_count(fov_ctx *ctx) {
+  if (!ctx) return 0;
+  DeviceGuard g(ctx);
+  if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) return 0;
+  ctx->prof.collect();
+  return (int)ctx->prof.totals.size();
+}
+
+int fov_profile_get(fov_ctx *ctx, int index, char *name, size_t name_cap, double *total_ms,
+                    uint64_t *launches) {
+  FOV_REQUIRE_CTX(ctx);
+  if (index < 0 || index >= (int)ctx->prof.totals.size())
+    return fail(ctx, FOV_ERR_INVALID, "fov_profile_get: index out of range");
+  auto it = ctx->prof.totals.begin();
+  std::advance(it, index);
+  if (name && name_cap) {
+    strncpy(name, it->first.c_str(), name_cap - 1);
+    name[name_cap - 1] = 0;
+  }
+  if (total_ms) *total_ms = it->second.ms;
+  if (launches) *launches = it->second.launches;
+  return FOV_OK;
+}
+
+int fov_malloc(fov_ctx *ctx, void **dptr, size_t nbytes) {
+  FOV_REQUIRE_CTX(ctx);
+  if (!dptr) return fail(ctx, FOV_ERR_INVALID, "fov_malloc: null output pointer");
+  DeviceGuard g(ctx);
+  FOV_CUDA(ctx, cudaMalloc(dptr, nbytes ? nbytes : 1), "fov_malloc");
+  return FOV_OK;
+}
+
+int fov_free(fov_ctx *ctx, void *dptr) {
+  FOV_REQUIRE_CTX(ctx);
+  DeviceGuard g(ctx);
+  FOV_CUDA(ctx, cudaStreamSynchronize(ctx->stream), "fov_free");
+  FOV_CUDA(ctx, cudaFree(dptr), "fov_free");
+  return FOV_OK;
+}
+
+int fov_memset(fov_ctx *ctx, void *dptr, int byte, size_t nbytes) {
+  FOV_REQUIRE_CTX(ctx);
+  DeviceGuard g(ctx);
+  FOV_CUDA(ctx, cudaMemsetAsync(dptr, byte, nbytes, ctx->stream), "fov_memset");
+  return FOV_OK;
+}
+
+int fov_memcpy_h2d(fov_ctx *ctx, void *dst, const void *src, size_t nbytes) {
+  FOV_REQUIRE_CTX(ctx);
+  DeviceGuard g(ctx);
+  FOV_CUDA(ctx, cudaMemcpyAsync(dst, src, nbytes, cudaMemcpyHostToDevice, ctx->stream),
+           "fov_memcpy_h2d");
+  FOV_CUDA(ctx, cudaStreamSynchronize(ctx->stream), "fov_memcpy_h2d");
+  return FOV_OK;
+}
+
+int fov_memcpy_d2h(fov_ctx *ctx, void *dst, const void *src, size_t nbytes) {
+  FOV_REQUIRE_CTX(ctx);
+  DeviceGuard g(ctx);
+  FOV_CUDA(ctx, cudaMemcpyAsync(dst, src, nbytes, cudaMemcpyDeviceToHost, ctx->stream),
+           "fov_memcpy_d2h");
+  FOV_CUDA(ctx, cudaStreamSynchronize(ctx->stream), "fov_memcpy_d2h");
+  return FOV_OK;
+}
+
+int fov_memcpy_h2d_async(fov_ctx *ctx, void *dst, const void *src, size_t nbytes) {
+  FOV_REQUIRE_CTX(ctx);
+  DeviceGuard g(ctx);
+  FOV_CUDA(ctx, cudaMemcpyAsync(dst, src, nbytes, cudaMemcpyHostToDevice, ctx->stream),
+           "fov_memcpy_h2d_async");
+  return FOV_OK;
+}
+
+int fov_memcpy_d2h_async(fov_ctx *ctx, void *dst, const void *src, size_t nbytes) {
+  FOV_REQUIRE_CTX(ctx);
+  DeviceGuard g(ctx);
+  FOV_CUDA(ctx, cudaMemcpyAsync(dst, src, nbytes, cudaMemcpyDeviceToHost, ctx->stream),
+           "fov_memcpy_d2h_async");
+  return FOV_OK;
+}
+
+int fov_host_alloc(fov_ctx *ctx, void **hptr, size_t nbytes) {
+  FOV_REQUIRE_CTX(ctx);
+  if (!hptr) return fail(ctx, FOV_ERR_INVALID, "fov_host_alloc: null output pointer");
+  DeviceGuard g(ctx);
+  FOV_CUDA(ctx, cudaHostAlloc(hptr, nbytes ? nbytes : 1, cudaHostAllocDefault), "fov_host_alloc");
+  return FOV_OK;
+}
+
+int fov_host_free(fov_ctx *ctx, void *hptr) {
+  FOV_REQUIRE_CTX(ctx);
+  DeviceGuard g(ctx);
+  FOV_CUDA(ctx, cudaFreeHost(hptr), "fov_host_free");
+  return FOV_OK;
+}
+
+// ---- SATEncoder ---------------------------------------------------------------------------
+
+int fov_sat_encode_batched(fov_ctx *ctx, int n, uint32_t *sat, size_t sat_stride,
+                           const uint8_t *src, size_t src_stride, int W, int H, int linesize) {
+  FOV_REQUIRE_CTX(ctx);
+  if (n <= 0 || !sat || !src || W <= 0 || H <= 0 || linesize < 3 * W || linesize / W < 3)
+    return fail(ctx, FOV_ERR_INVALID, "fov_sat_encode: invalid arguments");
+  if (((uintptr_t)sat % 4) != 0 || (sat_stride % 4) != 0)
+    return fail(ctx, FOV_ERR_INVALID, "fov_sat_encode: SAT buffer must be 4-byte aligned");
+  if (n > 65535) return fail(ctx, FOV_ERR_INVALID, "fov_sat_encode: batch too large");
+  DeviceGuard g(ctx);
+  int rc = ensure_sat_scratch(ctx, n, W, H);
+  if (rc) return rc;
+  FOV_CUDA(ctx,
+           launch_sat_encode(ctx->lc(), n, sat, sat_stride, src, src_stride, W, H, linesize,
+                             ctx->sat_scratch.base),
+           "sat encode launch");
+  return FOV_OK;
+}
+
+int fov_sat_encode(fov_ctx *ctx, uint32_t *sat, const uint8_t *src, int W, int H, int linesize) {
+  return fov_sat_encode_batched(ctx, 1, sat, 0, src, 0, W, H, linesize);
+}
+
+// ---- SATDecoder ---------------------------------------------------------------------------
+
+int fov_sat_grid_init(fov_ctx *ctx, int ow, int oh, int W, int H) {
+  FOV_REQUIRE_CTX(ctx);
+  DeviceGuard g(ctx);
+  const SatGrid *grid = nullptr;
+  int rc = get_sat_grid(ctx, ow, oh, W, H, &grid);
+  if (rc) return rc;
+  ctx->cur_sat_grid = grid;
+  const InterpLut *lut = nullptr;
+  return get_interp_lut(ctx, W, H, ow, oh, &lut);  // warm the inverse-warp table as well
+}
+
+int fov_sat_grid_export(fov_ctx *ctx, int16_t *host_grid, int ow, int oh, int W, int H) {
+  FOV_REQUIRE_CTX(ctx);
+  if (!host_grid) return fail(ctx, FOV_ERR_INVALID, "fov_sat_grid_export: null pointer");
+  DeviceGuard g(ctx);
+  const SatGrid *grid = nullptr;
+  int rc = get_sat_grid(ctx, ow, oh, W, H, &grid);
+  if (rc) return rc;
+  // Round-trip through the device copies so the export checks what the kernels actually read.
+  std::vector<int16_t> xe(ow + 1), ye(oh + 1);
+  FOV_CUDA(ctx, cudaMemcpy(xe.data(), grid->d_xedge, xe.size() * 2, cudaMemcpyDeviceToHost),
+           "grid export");
+  FOV_CUDA(ctx, cudaMemcpy(ye.data(), grid->d_yedge, ye.size() * 2, cudaMemcpyDeviceToHost),
+           "grid export");
+  for (int ty = 0; ty <= oh; ++ty)
+    for (int tx = 0; tx <= ow; ++tx) {
+      host_grid[((size_t)ty * (ow + 1) + tx) * 2] = xe[tx];
+      host_grid[((size_t)ty * (ow + 1) + tx) * 2 + 1] = ye[ty];
+    }
+  return FOV_OK;
+}
+
+int fov_sat_sample_rect_batched(fov_ctx *ctx, int n, uint8_t *out, size_t out_stride, int ow,
+                                int oh, int out_linesize, const uint32_t *sat, size_t sat_stride,
+                                int W, int H, const float *gaze_xy) {
+  FOV_REQUIRE_CTX(ctx);
+  if (n <= 0 || !out || !sat || !gaze_xy || ow <= 0 || oh <= 0 || out_linesize < 4 * ow ||
+      (out_linesize % 4) != 0 || ((uintptr_t)out % 4) != 0 || (out_stride % 4) != 0 ||
+      ((uintptr_t)sat % 4) != 0 || (sat_stride % 4) != 0 || W < 2 || H < 2)
+    return fail(ctx, FOV_ERR_INVALID, "fov_sat_sample_rect: invalid arguments");
+  DeviceGuard g(ctx);
+  const SatGrid *grid = nullptr;
+  int rc = get_sat_grid(ctx, ow, oh, W, H, &grid);  // lazy init, sat_decoder.cc:312-317
+  if (rc) return rc;
+  ctx->cur_sat_grid = grid;
+  for (int f0 = 0; f0 < n; f0 += kMaxBatchPerLaunch) {
+    const int m = n - f0 < kMaxBatchPerLaunch ? n - f0 : kMaxBatchPerLaunch;
+    GazeBatch gz;
+    memcpy(gz.xy, gaze_xy + 2 * (size_t)f0, sizeof(float) * 2 * m);
+    FOV_CUDA(ctx,
+             launch_sat_sample_rect(
+                 ctx->lc(), m, out + (size_t)f0 * out_stride, out_stride, ow, oh, out_linesize,
+                 reinterpret_cast<const uint32_t *>(reinterpret_cast<const uint8_t *>(sat) +
+                                                    (size_t)f0 * sat_stride),
+                 sat_stride, W, H, grid->d_xedge, grid->d_yedge, gz),
+             "sample_rect launch");
+  }
+  return FOV_OK;
+}
+
+int fov_sat_sample_rect(fov_ctx *ctx, uint8_t *out, int ow, int oh, int out_linesize,
+                        const uint32_t *sat, int W, int H, float cx, float cy) {
+  const float gz[2] = {cx, cy};
+  return fov_sat_sample_rect_batched(ctx, 1, out, 0, ow, oh, out_linesize, sat, 0, W, H, gz);
+}
+
+int fov_sat_interpolate_rect_batched(fov_ctx *ctx, int n, uint8_t *out, size_t out_stride, int W,
+                                     int H, const uint8_t *red, size_t red_stride, int ow, int oh,
+                                     const float *gaze_xy) {
+  FOV_REQUIRE_CTX(ctx);
+  if (n <= 0 || !out || !red || !gaze_xy || ((uintptr_t)out % 4) != 0 || (out_stride % 4) != 0 ||
+      ((uintptr_t)red % 4) != 0 || (red_stride % 4) != 0)
+    return fail(ctx, FOV_ERR_INVALID, "fov_sat_interpolate_rect: invalid arguments");
+  DeviceGuard g(ctx);
+  const InterpLut *lut = nullptr;
+  int rc = get_interp_lut(ctx, W, H, ow, oh, &lut);
+  if (rc) return rc;
+  for (int f0 = 0; f0 < n; f0 += kMaxBatchPerLaunch) {
+    const int m = n - f0 < kMaxBatchPerLaunch ? n - f0 : kMaxBatchPerLaunch;
+    GazeBatch gz;
+    memcpy(gz.xy, gaze_xy + 2 * (size_t)f0, sizeof(float) * 2 * m);
+    FOV_CUDA(ctx,
+             launch_sat_interpolate_rect(ctx->lc(), m, out + (size_t)f0 * out_stride, out_stride,
+                                         W, H, red + (size_t)f0 * red_stride, red_stride, ow, oh,
+                                         lut->d_x, lut->d_y, gz),
+             "interpolate_rect launch");
+  }
+  return FOV_OK;
+}
+
+int fov_sat_interpolate_rect(fov_ctx *ctx, uint8_t *out, int W, int H, int out_linesize,
+                             const uint8_t *red, int ow, int oh, int red_linesize, float cx,
+                             float cy) {
+  (void)out_linesize;  // unused by the reference kernel as well (sat_decoder.cc:902-912)
+  (void)red_linesize;
+  const float gz[2] = {cx, cy};
+  return fov_sat_interpolate_rect_batched(ctx, 1, out, 0, W, H, red, 0, ow, oh, gz);
+}
+
+int fov_sat_decode(fov_ctx *ctx, uint8_t *out, int out_linesize, const uint32_t *sat, int W,
+                   int H) {
+  FOV_REQUIRE_CTX(ctx);
+  if (!out || !sat || W <= 0 || H <= 0 || out_linesize / W < 3)
+    return fail(ctx, FOV_ERR_INVALID, "fov_sat_decode: invalid arguments");
+  DeviceGuard g(ctx);
+  FOV_CUDA(ctx, launch_sat_decode(ctx->lc(), out, out_linesize, sat, W, H), "decode launch");
+  return FOV_OK;
+}
+
+int fov_sat_foveate_batched(fov_ctx *ctx, int n, uint8_t *full_out, size_t full_stride,
+                            uint8_t *reduced, size_t red_stride, uint32_t *sat, size_t sat_stride,
+                            const uint8_t *src, size_t src_stride, int W, int H, int linesize,
+                            int ow, int oh, const float *gaze_xy) {
+  int rc = fov_sat_encode_batched(ctx, n, sat, sat_stride, src, src_stride, W, H, linesize);
+  if (rc) return rc;
+  rc = fov_sat_sample_rect_batched(ctx, n, reduced, red_stride, ow, oh, 4 * ow, sat, sat_stride, W,
+                                   H, gaze_xy);
+  if (rc) return rc;
+  return fov_sat_interpolate_rect_batched(ctx, n, full_out, full_stride, W, H, reduced, red_stride,
+                                          ow, oh, gaze_xy);
+}
+
+// ---- ImageSampler ---------------------------------------------------------------------------
+
+int fov_img_grid_init(fov_ctx *ctx, int ow, int oh, int W, int H) {
+  FOV_REQUIRE_CTX(ctx);
+  DeviceGuard g(ctx);
+  const ImgGrid *grid = nullptr;
+  return get_img_grid(ctx, ow, oh, W, H, &grid);
+}
+
+int fov_img_grid_export(fov_ctx *ctx, int16_t *host_grid, int ow, int oh, int W, int H) {
+  FOV_REQUIRE_CTX(ctx);
+  if (!host_grid) return fail(ctx, FOV_ERR_INVALID, "fov_img_grid_export: null pointer");
+  DeviceGuard g(ctx);
+  const ImgGrid *grid = nullptr;
+  int rc = get_img_grid(ctx, ow, oh, W, H, &grid);
+  if (rc) return rc;
+  std::vector<int16_t> xd(ow), yd(oh);
+  FOV_CUDA(ctx, cudaMemcpy(xd.data(), grid->d_xd, xd.size() * 2, cudaMemcpyDeviceToHost),
+           "grid export");
+  FOV_CUDA(ctx, cudaMemcpy(yd.data(), grid->d_yd, yd.size() * 2, cudaMemcpyDeviceToHost),
+           "grid export");
+  for (int j = 0; j < oh; ++j)
+    for (int i = 0; i < ow; ++i) {
+      host_grid[((size_t)j * ow + i) * 2] = xd[i];
+      host_grid[((size_t)j * ow + i) * 2 + 1] = yd[j];
+    }
+  return FOV_OK;
+}
+
+static bool gather_args_ok(const uint8_t *out, int ow, int oh, int out_linesize, const uint8_t *src,
+                           int W, int H, int src_linesize) {
+  return out && src && ow > 0 && oh > 0 && W > 0 && H > 0 && out_linesize / ow >= 3 &&
+         src_linesize / W >= 3;
+}
+
+int fov_img_sample_rect(fov_ctx *ctx, uint8_t *out, int ow, int oh, int out_linesize,
+                        const uint8_t *src, int W, int H, int src_linesize, float cx, float cy) {
+  FOV_REQUIRE_CTX(ctx);
+  if (!gather_args_ok(out, ow, oh, out_linesize, src, W, H, src_linesize))
+    return fail(ctx, FOV_ERR_INVALID, "fov_img_sample_rect: invalid arguments");
+  DeviceGuard g(ctx);
+  const ImgGrid *grid = nullptr;
+  int rc = get_img_grid(ctx, ow, oh, W, H, &grid);
+  if (rc) return rc;
+  FOV_CUDA(ctx,
+           launch_img_sample_rect(ctx->lc(), out, ow, oh, out_linesize, src, W, H, src_linesize,
+                                  grid->d_xd, grid->d_yd, cx, cy),
+           "img sample_rect launch");
+  return FOV_OK;
+}
+
+int fov_img_logpolar_grid_init(fov_ctx *ctx, int ow, int oh, int W, int H) {
+  FOV_REQUIRE_CTX(ctx);
+  (void)W;  // the log-polar radius is in source pixels and does not depend on W, H
+  (void)H;
+  DeviceGuard g(ctx);
+  const LogpolarGrid *grid = nullptr;
+  return get_lp_grid(ctx, ow, oh, &grid);
+}
+
+int fov_img_logpolar_grid_export(fov_ctx *ctx, int16_t *host_grid, int ow, int oh) {
+  FOV_REQUIRE_CTX(ctx);
+  if (!host_grid) return fail(ctx, FOV_ERR_INVALID, "fov_img_logpolar_grid_export: null pointer");
+  DeviceGuard g(ctx);
+  const LogpolarGrid *grid = nullptr;
+  int rc = get_lp_grid(ctx, ow, oh, &grid);
+  if (rc) return rc;
+  int16_t *d = nullptr;
+  const size_t bytes = (size_t)ow * oh * 2 * sizeof(int16_t);
+  FOV_CUDA(ctx, cudaMalloc(reinterpret_cast<void **>(&d), bytes), "logpolar export alloc");
+  cudaError_t e = launch_img_logpolar_grid_expand(ctx->lc(), d, ow, oh, grid->d_radius,
+                                                  grid->d_cos, grid->d_sin);
+  if (e == cudaSuccess)
+    e = cudaMemcpyAsync(host_grid, d, bytes, cudaMemcpyDeviceToHost, ctx->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  cudaFree(d);
+  FOV_CUDA(ctx, e, "logpolar export");
+  return FOV_OK;
+}
+
+int fov_img_sample_logpolar(fov_ctx *ctx, uint8_t *out, int ow, int oh, int out_linesize,
+                            const uint8_t *src, int W, int H, int src_linesize, float cx,
+                            float cy) {
+  FOV_REQUIRE_CTX(ctx);
+  if (!gather_args_ok(out, ow, oh, out_linesize, src, W, H, src_linesize))
+    return fail(ctx, FOV_ERR_INVALID, "fov_img_sample_logpolar: invalid arguments");
+  DeviceGuard g(ctx);
+  const LogpolarGrid *grid = nullptr;
+  int rc = get_lp_grid(ctx, ow, oh, &grid);
+  if (rc) return rc;
+  FOV_CUDA(ctx,
+           launch_img_sample_logpolar(ctx->lc(), out, ow, oh, out_linesize, src, W, H,
+                                      src_linesize, grid->d_radius, grid->d_cos, grid->d_sin, cx,
+                                      cy),
+           "img sample_logpolar launch");
+  return FOV_OK;
+}
+
+int fov_img_interpolate_logpolar(fov_ctx *ctx, uint8_t *out, int W, int H, int out_linesize,
+                                 const uint8_t *red, int ow, int oh, int red_linesize, float cx,
+                                 float cy) {
+  FOV_REQUIRE_CTX(ctx);
+  (void)out_linesize;  // unused by the reference kernel as well (image_sampler.cc:794-803)
+  (void)red_linesize;
+  if (!out || !red || W <= 0 || H <= 0 || ow <= 0 || oh <= 0 || ((uintptr_t)out % 4) != 0 ||
+      ((uintptr_t)red % 4) != 0)
+    return fail(ctx, FOV_ERR_INVALID, "fov_img_interpolate_logpolar: invalid arguments");
+  DeviceGuard g(ctx);
+  FOV_CUDA(ctx, launch_img_interpolate_logpolar(ctx->lc(), out, W, H, red, ow, oh, cx, cy),
+           "img interpolate_logpolar launch");
+  return FOV_OK;
+}
+
+int fov_img_logpolar_blur(fov_ctx *ctx, uint8_t *out, int ow, int oh, int linesize,
+                          const uint8_t *src) {
+  FOV_REQUIRE_CTX(ctx);
+  (void)linesize;  // dense uchar3 addressing in the reference kernel
+  if (!out || !src || ow <= 0 || oh <= 0 || ((uintptr_t)out % 4) != 0 || ((uintptr_t)src % 4) != 0)
+    return fail(ctx, FOV_ERR_INVALID, "fov_img_logpolar_blur: invalid arguments");
+  DeviceGuard g(ctx);
+  FOV_CUDA(ctx, launch_img_logpolar_blur(ctx->lc(), out, ow, oh, src), "img blur launch");
+  return FOV_OK;
+}
+
+int fov_reduced_dim(int full_dim) {
+  // 16 * ceil(dim / 1.8 / 16), run_satlogrectilinear.cc:113-114
+  return 16 * (int)std::ceil(full_dim / 1.8 / 16);
+}
+
+}  // extern "C"

@@ -1,0 +1,168 @@
+// Internal declarations shared by the translation units of libfov360.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <map>
+#include <string>
+#include <tuple>
+#include <vector>
+
+#include "fov360.h"
+
+namespace fov {
+
+constexpr int kMaxBatchPerLaunch = 64;  // gaze points carried by value in kernel params
+
+// ---- per-axis lookup tables (built on the host, see luts.cc) -----------------------------
+
+// One entry of the inverse-warp table, indexed by (pos - centre) + n_full.
+// Everything interpolate_rect_kernel derives from one axis, minus the two gaze-dependent
+// border fix-ups (sat_decoder_interpolate_kernel.cl:105-116) that the kernel applies inline.
+struct __align__(16) InterpEntry {
+  int16_t idx_exact;  // clamp(u + n_red/2, 0, n_red-1)               (:69-70)
+  int16_t min_u;      // min(u, u+du)                                    (:100-103)
+  int16_t max_u;      // max(u, u+du)
+  int16_t exact;      // delta_calculated == delta                      (:67)
+  int16_t rel_lo;     // min(d_min, d_calc): lo = centre + rel_lo       (:91-98)
+  int16_t rel_hi;     // max(d_min, d_calc)
+  float ratio;        // clamp((d - rel_lo) / (rel_hi - rel_lo), 0, 1)  (:135-142)
+};
+static_assert(sizeof(InterpEntry) == 16, "InterpEntry must be 16 bytes");
+
+struct SatGrid {  // SATDecoder grid, separable form
+  int ow, oh, W, H;
+  int16_t *d_xedge = nullptr;  // [ow+1]
+  int16_t *d_yedge = nullptr;  // [oh+1]
+  std::vector<int16_t> h_xedge, h_yedge;
+};
+
+struct InterpLut {  // SATDecoder inverse warp, separable form
+  int W, H, ow, oh;
+  InterpEntry *d_x = nullptr;  // [2W+1], index = dx + W
+  InterpEntry *d_y = nullptr;  // [2H+1], index = dy + H
+};
+
+struct ImgGrid {  // ImageSampler log-rect grid, separable form
+  int ow, oh, W, H;
+  int16_t *d_xd = nullptr;  // [ow]
+  int16_t *d_yd = nullptr;  // [oh]
+  std::vector<int16_t> h_xd, h_yd;
+};
+
+struct LogpolarGrid {  // ImageSampler log-polar grid, separable factors
+  int ow, oh;
+  float *d_radius = nullptr;  // [ow]
+  float *d_cos = nullptr;     // [oh]
+  float *d_sin = nullptr;     // [oh]
+  std::vector<float> h_radius, h_cos, h_sin;
+};
+
+// Host-side table builders (luts.cc).  Plain C++ + libm, no CUDA.
+void build_sat_grid_edges(int ow, int oh, int W, int H, std::vector<int16_t> &xe,
+                          std::vector<int16_t> &ye);
+void build_interp_axis(int n_full, int n_red, std::vector<InterpEntry> &lut);
+void build_img_grid_axes(int ow, int oh, int W, int H, std::vector<int16_t> &xd,
+                         std::vector<int16_t> &yd);
+void build_logpolar_axes(int ow, int oh, std::vector<float> &radius, std::vector<float> &cs,
+                         std::vector<float> &sn);
+
+// ---- launch context: stream + optional per-kernel event timing ------------------------------
+
+// Per-kernel CUDA-event timing (the analogue of CL_QUEUE_PROFILING_ENABLE, which the reference
+// never switches on, opencl_manager.cc:55).  Off by default: no events are recorded.
+struct Profiler {
+  struct Pending {
+    const char *name;
+    cudaEvent_t a, b;
+  };
+  struct Total {
+    double ms = 0;
+    uint64_t launches = 0;
+  };
+  bool enabled = false;
+  std::vector<Pending> pending;
+  std::vector<cudaEvent_t> pool;
+  std::map<std::string, Total> totals;
+  cudaEvent_t get();
+  void collect();  // requires the stream to be idle
+  void release();
+};
+
+struct LaunchCtx {
+  cudaStream_t stream = nullptr;
+  int sm_count = 148;
+  Profiler *prof = nullptr;
+  uint64_t *launches = nullptr;
+};
+
+// RAII bracket around ONE kernel launch: counts it and, when profiling, times it.
+class KernelScope {
+ public:
+  KernelScope(const LaunchCtx &lc, const char *name) : lc_(lc) {
+    if (lc.launches) ++*lc.launches;
+    if (lc.prof && lc.prof->enabled) {
+      p_.name = name;
+      p_.a = lc.prof->get();
+      p_.b = lc.prof->get();
+      cudaEventRecord(p_.a, lc.stream);
+      on_ = true;
+    }
+  }
+  ~KernelScope() {
+    if (on_) {
+      cudaEventRecord(p_.b, lc_.stream);
+      lc_.prof->pending.push_back(p_);
+    }
+  }
+
+ private:
+  const LaunchCtx &lc_;
+  Profiler::Pending p_{};
+  bool on_ = false;
+};
+
+// ---- kernel launchers (one per .cu) ----------------------------------------------------------
+
+struct GazeBatch {
+  float xy[2 * kMaxBatchPerLaunch];
+};
+
+// SAT build scratch: carry tables sized for (n, W, H); owned by the context.
+struct SatScratch {
+  void *base = nullptr;
+  size_t bytes = 0;
+};
+size_t sat_scratch_bytes(int n, int W, int H);
+cudaError_t launch_sat_encode(const LaunchCtx &lc, int n, uint32_t *sat, size_t sat_stride,
+                              const uint8_t *src, size_t src_stride, int W, int H, int linesize,
+                              void *scratch);
+
+cudaError_t launch_sat_sample_rect(const LaunchCtx &lc, int n, uint8_t *out, size_t out_stride, int ow,
+                                   int oh, int out_linesize, const uint32_t *sat,
+                                   size_t sat_stride, int W, int H, const int16_t *xedge,
+                                   const int16_t *yedge, const GazeBatch &gaze);
+cudaError_t launch_sat_interpolate_rect(const LaunchCtx &lc, int n, uint8_t *out, size_t out_stride,
+                                        int W, int H, const uint8_t *red, size_t red_stride,
+                                        int ow, int oh, const InterpEntry *lx,
+                                        const InterpEntry *ly, const GazeBatch &gaze);
+cudaError_t launch_sat_decode(const LaunchCtx &lc, uint8_t *out, int out_linesize, const uint32_t *sat,
+                              int W, int H);
+
+cudaError_t launch_img_sample_rect(const LaunchCtx &lc, uint8_t *out, int ow, int oh, int out_linesize,
+                                   const uint8_t *src, int W, int H, int src_linesize,
+                                   const int16_t *xd, const int16_t *yd, float cx, float cy);
+cudaError_t launch_img_sample_logpolar(const LaunchCtx &lc, uint8_t *out, int ow, int oh,
+                                       int out_linesize, const uint8_t *src, int W, int H,
+                                       int src_linesize, const float *radius, const float *cs,
+                                       const float *sn, float cx, float cy);
+cudaError_t launch_img_interpolate_logpolar(const LaunchCtx &lc, uint8_t *out, int W, int H,
+                                            const uint8_t *red, int ow, int oh, float cx,
+                                            float cy);
+cudaError_t launch_img_logpolar_blur(const LaunchCtx &lc, uint8_t *out, int ow, int oh,
+                                     const uint8_t *src);
+cudaError_t launch_img_logpolar_grid_expand(const LaunchCtx &lc, int16_t *grid, int ow, int oh,
+                                            const float *radius, const float *cs,
+                                            const float *sn);
+
+}  // namespace fov

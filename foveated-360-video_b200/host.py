@@ -1,0 +1,316 @@
+"""Host-side mirror of the reference's foveation classes over the C ABI (tests / bench harness).
+
+Class and method names follow the reference (src/opencl_manager.h:8-22, src/sat_encoder.h:21-43,
+src/sat_decoder.h:20-83, src/image_sampler.h:29-102); argument order and meaning are the
+reference's: sizes in pixels, linesizes in bytes, gaze as two floats in [0,1].  ``cl_mem``
+handles become :class:`DeviceBuffer` objects (a device pointer + size).  The shipped drop-in for
+the reference's C++ call sites is include/fov360/*.h; this module exists so that the parity tests
+read like the reference's call sequences (video_server.cc:296-345, run_satlogrectilinear.cc:915-949).
+
+Every method ends in a launch on the manager's stream (the in-order command queue); results are
+visible after ``Finish()`` or a blocking ``copy_to_host``.  Errors raise :class:`FovError` - the
+reference prints to stderr and returns; a Python caller is better served by an exception.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _capi
+
+
+class FovError(RuntimeError):
+    pass
+
+
+class DeviceBuffer:
+    """cl::Buffer(context, CL_MEM_READ_WRITE, nbytes) (video_server.cc:224-232)."""
+
+    def __init__(self, manager: "OpenCLManager", nbytes: int):
+        self.manager = manager
+        self.nbytes = int(nbytes)
+        p = C.c_void_p()
+        manager._check(manager.lib.fov_malloc(manager.ctx, C.byref(p), self.nbytes))
+        self.ptr = p.value
+
+    def __call__(self):  # cl::Buffer::operator() -> cl_mem
+        return self.ptr
+
+    def at(self, byte_offset: int) -> int:
+        return self.ptr + int(byte_offset)
+
+    def free(self) -> None:
+        if self.ptr:
+            self.manager.lib.fov_free(self.manager.ctx, self.ptr)
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            if self.manager.ctx:
+                self.free()
+        except Exception:
+            pass
+
+
+def _ptr(buf) -> int:
+    if isinstance(buf, DeviceBuffer):
+        return buf.ptr
+    return int(buf)
+
+
+class OpenCLManager:
+    """Device / stream holder; replaces OpenCLManager::InitializeContext (opencl_manager.cc:7-67)."""
+
+    def __init__(self, device: int = 0):
+        self.lib = _capi.load()
+        self.ctx = None
+        self.device = device
+
+    def InitializeContext(self) -> None:
+        err = C.c_int(0)
+        ctx = self.lib.fov_ctx_create(self.device, C.byref(err))
+        if not ctx:
+            raise FovError("fov_ctx_create(%d) failed (%d): %s" % (
+                self.device, err.value, self.lib.fov_last_error_string(None).decode()))
+        self.ctx = ctx
+
+    # -- helpers ------------------------------------------------------------------------
+    def _check(self, rc: int) -> None:
+        if rc != 0:
+            msg = self.lib.fov_last_error_string(self.ctx if rc != -1 else None)
+            raise FovError("fov360 error %d: %s" % (rc, (msg or b"").decode()))
+
+    @property
+    def stream(self) -> int:
+        return self.lib.fov_ctx_stream(self.ctx) or 0
+
+    @property
+    def launch_count(self) -> int:
+        return int(self.lib.fov_ctx_launch_count(self.ctx))
+
+    def profile(self, on: bool) -> None:
+        self._check(self.lib.fov_profile_enable(self.ctx, int(on)))
+
+    def profile_reset(self) -> None:
+        self._check(self.lib.fov_profile_reset(self.ctx))
+
+    def profile_totals(self) -> dict:
+        """{kernel name: (total ms, launches)} since the last reset (synchronises the stream)."""
+        out = {}
+        name = C.create_string_buffer(64)
+        ms, cnt = C.c_double(0), C.c_uint64(0)
+        for i in range(self.lib.fov_profile_count(self.ctx)):
+            self._check(self.lib.fov_profile_get(self.ctx, i, name, 64, C.byref(ms), C.byref(cnt)))
+            out[name.value.decode()] = (ms.value, int(cnt.value))
+        return out
+
+    def Buffer(self, nbytes: int) -> DeviceBuffer:
+        return DeviceBuffer(self, nbytes)
+
+    def copy_to_device(self, dst, host: np.ndarray, dst_offset: int = 0) -> None:
+        """cl::copy(queue, begin, end, buffer): blocking (video_server.cc:297-299)."""
+        host = np.ascontiguousarray(host)
+        self._check(self.lib.fov_memcpy_h2d(self.ctx, _ptr(dst) + dst_offset, host.ctypes.data,
+                                            host.nbytes))
+
+    def copy_to_host(self, host: np.ndarray, src, src_offset: int = 0) -> np.ndarray:
+        """cl::copy(queue, buffer, begin, end): blocking (video_server.cc:342-345)."""
+        assert host.flags["C_CONTIGUOUS"]
+        self._check(self.lib.fov_memcpy_d2h(self.ctx, host.ctypes.data, _ptr(src) + src_offset,
+                                            host.nbytes))
+        return host
+
+    def upload(self, host: np.ndarray) -> DeviceBuffer:
+        buf = self.Buffer(host.nbytes)
+        self.copy_to_device(buf, host)
+        return buf
+
+    def memset(self, dst, byte: int, nbytes: int, offset: int = 0) -> None:
+        self._check(self.lib.fov_memset(self.ctx, _ptr(dst) + offset, byte, nbytes))
+
+    def Finish(self) -> None:
+        """clFlush + clFinish (video_server.cc:302-303)."""
+        self._check(self.lib.fov_sync(self.ctx))
+
+    def close(self) -> None:
+        if self.ctx:
+            self.lib.fov_ctx_destroy(self.ctx)
+            self.ctx = None
+
+
+def _gaze_array(gaze) -> np.ndarray:
+    g = np.ascontiguousarray(np.asarray(gaze, dtype=np.float32).reshape(-1, 2))
+    return g
+
+
+class SATEncoder:
+    """sat_encoder.h:21-43."""
+
+    def __init__(self, cl_manager: OpenCLManager | None = None):
+        self.m = cl_manager
+
+    def _need(self):
+        if self.m is None or not self.m.ctx:
+            raise FovError("Not initialized with OpenCL")  # sat_encoder.cc:70-74
+
+    def EncodeFrameGPU(self, target_buffer, source_buffer, width, height, source_linesize):
+        self._need()
+        self.m._check(self.m.lib.fov_sat_encode(self.m.ctx, _ptr(target_buffer),
+                                                _ptr(source_buffer), width, height,
+                                                source_linesize))
+
+    def EncodeFramesGPU(self, n, target_buffer, target_stride, source_buffer, source_stride, width,
+                        height, source_linesize):
+        """Batched form: n independent frames, strides in bytes (no reference counterpart)."""
+        self._need()
+        self.m._check(self.m.lib.fov_sat_encode_batched(
+            self.m.ctx, n, _ptr(target_buffer), target_stride, _ptr(source_buffer), source_stride,
+            width, height, source_linesize))
+
+
+class SATDecoder:
+    """sat_decoder.h:20-83 (log-rectilinear sampler / inverse warp / exact decode)."""
+
+    def __init__(self, cl_manager: OpenCLManager | None = None):
+        self.m = cl_manager
+
+    def _need(self):
+        if self.m is None or not self.m.ctx:
+            raise FovError("Not initialized with OpenCL")  # sat_decoder.cc:179-183
+
+    def InitializeGrid(self, target_width, target_height, source_width, source_height):
+        self._need()
+        self.m._check(self.m.lib.fov_sat_grid_init(self.m.ctx, target_width, target_height,
+                                                   source_width, source_height))
+
+    def ExportGrid(self, target_width, target_height, source_width, source_height) -> np.ndarray:
+        """The reference's int16 [(oh+1)][(ow+1)][2] grid buffer, for parity checks."""
+        self._need()
+        g = np.zeros((target_height + 1, target_width + 1, 2), np.int16)
+        self.m._check(self.m.lib.fov_sat_grid_export(self.m.ctx, g.ctypes.data, target_width,
+                                                     target_height, source_width, source_height))
+        return g
+
+    def SampleFrameRectGPU(self, target_buffer, target_width, target_height, target_linesize,
+                           source_buffer, source_width, source_height, center_x, center_y):
+        """`source_width/height` stand in for the AVCodecContext* (sat_decoder.cc:328-329)."""
+        self._need()
+        self.m._check(self.m.lib.fov_sat_sample_rect(
+            self.m.ctx, _ptr(target_buffer), target_width, target_height, target_linesize,
+            _ptr(source_buffer), source_width, source_height, center_x, center_y))
+
+    def SampleFramesRectGPU(self, n, target_buffer, target_stride, target_width, target_height,
+                            target_linesize, source_buffer, source_stride, source_width,
+                            source_height, gaze):
+        self._need()
+        g = _gaze_array(gaze)
+        assert g.shape[0] == n
+        self.m._check(self.m.lib.fov_sat_sample_rect_batched(
+            self.m.ctx, n, _ptr(target_buffer), target_stride, target_width, target_height,
+            target_linesize, _ptr(source_buffer), source_stride, source_width, source_height,
+            g.ctypes.data_as(C.POINTER(C.c_float))))
+
+    def InterpolateFrameRectGPU(self, target_buffer, target_width, target_height, target_linesize,
+                                source_buffer, source_width, source_height, source_linesize,
+                                center_x, center_y):
+        self._need()
+        self.m._check(self.m.lib.fov_sat_interpolate_rect(
+            self.m.ctx, _ptr(target_buffer), target_width, target_height, target_linesize,
+            _ptr(source_buffer), source_width, source_height, source_linesize, center_x, center_y))
+
+    def InterpolateFramesRectGPU(self, n, target_buffer, target_stride, target_width, target_height,
+                                 source_buffer, source_stride, source_width, source_height, gaze):
+        self._need()
+        g = _gaze_array(gaze)
+        assert g.shape[0] == n
+        self.m._check(self.m.lib.fov_sat_interpolate_rect_batched(
+            self.m.ctx, n, _ptr(target_buffer), target_stride, target_width, target_height,
+            _ptr(source_buffer), source_stride, source_width, source_height,
+            g.ctypes.data_as(C.POINTER(C.c_float))))
+
+    def DecodeFrameGPU(self, target_buffer, target_linesize, source_buffer, width, height):
+        self._need()
+        self.m._check(self.m.lib.fov_sat_decode(self.m.ctx, _ptr(target_buffer), target_linesize,
+                                                _ptr(source_buffer), width, height))
+
+
+def FoveateFramesGPU(m: OpenCLManager, n, full_out, full_stride, reduced, reduced_stride, sat,
+                     sat_stride, source, source_stride, width, height, source_linesize, ow, oh,
+                     gaze):
+    """run_satlogrectilinear.cc:926-943 (encode -> sample -> interpolate) for n frames."""
+    g = _gaze_array(gaze)
+    assert g.shape[0] == n
+    m._check(m.lib.fov_sat_foveate_batched(
+        m.ctx, n, _ptr(full_out), full_stride, _ptr(reduced), reduced_stride, _ptr(sat),
+        sat_stride, _ptr(source), source_stride, width, height, source_linesize, ow, oh,
+        g.ctypes.data_as(C.POINTER(C.c_float))))
+
+
+class ImageSampler:
+    """image_sampler.h:29-102 (no-SAT baseline: log-rect point sampling and log-polar)."""
+
+    def __init__(self, cl_manager: OpenCLManager | None = None):
+        self.m = cl_manager
+
+    def _need(self):
+        if self.m is None or not self.m.ctx:
+            raise FovError("Not initialized with OpenCL")
+
+    def InitializeGrid(self, target_width, target_height, source_width, source_height):
+        self._need()
+        self.m._check(self.m.lib.fov_img_grid_init(self.m.ctx, target_width, target_height,
+                                                   source_width, source_height))
+
+    def ExportGrid(self, target_width, target_height, source_width, source_height) -> np.ndarray:
+        self._need()
+        g = np.zeros((target_height, target_width, 2), np.int16)
+        self.m._check(self.m.lib.fov_img_grid_export(self.m.ctx, g.ctypes.data, target_width,
+                                                     target_height, source_width, source_height))
+        return g
+
+    def InitializeLogpolarGrid(self, target_width, target_height, source_width, source_height):
+        self._need()
+        self.m._check(self.m.lib.fov_img_logpolar_grid_init(
+            self.m.ctx, target_width, target_height, source_width, source_height))
+
+    def ExportLogpolarGrid(self, target_width, target_height) -> np.ndarray:
+        self._need()
+        g = np.zeros((target_height, target_width, 2), np.int16)
+        self.m._check(self.m.lib.fov_img_logpolar_grid_export(self.m.ctx, g.ctypes.data,
+                                                              target_width, target_height))
+        return g
+
+    def SampleFrameRectGPU(self, target_buffer, target_width, target_height, target_linesize,
+                           source_buffer, source_width, source_height, source_linesize, center_x,
+                           center_y):
+        self._need()
+        self.m._check(self.m.lib.fov_img_sample_rect(
+            self.m.ctx, _ptr(target_buffer), target_width, target_height, target_linesize,
+            _ptr(source_buffer), source_width, source_height, source_linesize, center_x, center_y))
+
+    def SampleFrameLogPolarGPU(self, target_buffer, target_width, target_height, target_linesize,
+                               source_buffer, source_width, source_height, source_linesize,
+                               center_x, center_y):
+        self._need()
+        self.m._check(self.m.lib.fov_img_sample_logpolar(
+            self.m.ctx, _ptr(target_buffer), target_width, target_height, target_linesize,
+            _ptr(source_buffer), source_width, source_height, source_linesize, center_x, center_y))
+
+    def InterpolateFrameLogPolarGPU(self, target_buffer, target_width, target_height,
+                                    target_linesize, source_buffer, source_width, source_height,
+                                    source_linesize, center_x, center_y):
+        self._need()
+        self.m._check(self.m.lib.fov_img_interpolate_logpolar(
+            self.m.ctx, _ptr(target_buffer), target_width, target_height, target_linesize,
+            _ptr(source_buffer), source_width, source_height, source_linesize, center_x, center_y))
+
+    def ApplyLogPolarGaussianBlur(self, target_buffer, width, height, linesize, source_buffer):
+        self._need()
+        self.m._check(self.m.lib.fov_img_logpolar_blur(self.m.ctx, _ptr(target_buffer), width,
+                                                       height, linesize, _ptr(source_buffer)))
+
+
+def reduced_dim(full_dim: int) -> int:
+    """16*ceil(dim/1.8/16), run_satlogrectilinear.cc:113-114."""
+    return int(_capi.load().fov_reduced_dim(int(full_dim)))

@@ -1,0 +1,203 @@
+/*
+ * fov360.h - C ABI of the B200-native foveation transform (libfov360.so).
+ *
+ * This is the drop-in boundary for the per-frame foveation hot path of
+ * AugmentariumLab/foveated-360-video.  It replaces the reference's OpenCL layer
+ * (src/opencl_manager.{h,cc} + cl::Buffer / cl::copy at the call sites) and is what
+ * the C++ classes in include/fov360/*.h (SATEncoder / SATDecoder / ImageSampler /
+ * OpenCLManager, same names and signatures as the reference) are written against.
+ *
+ * Conventions (identical to the reference unless stated):
+ *   - widths/heights are in pixels, linesizes in BYTES, gaze is two floats in [0,1]
+ *     (x right, y down), pixel centre = (int)(c * dim)  (sat_decoder_sample_rect_kernel.cl:176);
+ *   - frames are RGB0 u8 (4 B/pixel; channel 3 is padding), the SAT is dense packed
+ *     u32[H][W][3] holding wrapping (mod 2^32) sums (sat_encoder.cc:77);
+ *   - every operation is enqueued asynchronously on the context's stream (the
+ *     reference's in-order command queue); results are visible after fov_sync() or a
+ *     blocking fov_memcpy_*;
+ *   - a context is thread-compatible (one context per thread), not thread-safe;
+ *   - all pointers passed to the fov_sat_* / fov_img_* entry points are DEVICE pointers
+ *     (fov_malloc) - they play the role of the reference's cl_mem handles;
+ *   - return value 0 = success, otherwise an FOV_ERR_* code (negative) or a positive
+ *     cudaError_t; fov_last_error_string() describes the last failure of a context.
+ *
+ * There is deliberately no CPU fallback: if no CUDA device is usable, fov_ctx_create
+ * fails and every other entry point returns FOV_ERR_NO_CONTEXT.
+ */
+#ifndef FOV360_H_
+#define FOV360_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FOV360_VERSION 100
+
+enum {
+  FOV_OK = 0,
+  FOV_ERR_NO_CONTEXT = -1,   /* ctx == NULL (the reference's "Not initialized with OpenCL") */
+  FOV_ERR_INVALID = -2,      /* bad size / pointer / linesize                                */
+  FOV_ERR_NO_DEVICE = -3,    /* no usable CUDA device: there is no CPU fallback              */
+  FOV_ERR_GRID = -4,         /* grid / LUT not initialised and cannot be derived             */
+  FOV_ERR_UNSUPPORTED = -5
+};
+
+typedef struct fov_ctx fov_ctx;
+
+/* ---- device runtime: replaces OpenCLManager (opencl_manager.h:8-22, .cc:7-67) ---------- */
+
+/* OpenCLManager::InitializeContext: binds `device`, creates the in-order stream. */
+fov_ctx *fov_ctx_create(int device, int *err);
+void fov_ctx_destroy(fov_ctx *ctx);
+/* OpenCLManager::GetCLErrorString analogue; ctx may be NULL (global creation errors). */
+const char *fov_last_error_string(const fov_ctx *ctx);
+int fov_device_count(void);
+int fov_ctx_device(const fov_ctx *ctx);
+/* The context's cudaStream_t (as void*), for callers that record their own CUDA events. */
+void *fov_ctx_stream(const fov_ctx *ctx);
+/* clFlush + clFinish (video_server.cc:302-303). */
+int fov_sync(fov_ctx *ctx);
+/* Number of kernels launched through this context so far (bench accounting). */
+uint64_t fov_ctx_launch_count(const fov_ctx *ctx);
+
+/* Per-kernel device timing (the role of CL_QUEUE_PROFILING_ENABLE + clGetEventProfilingInfo;
+ * the reference creates its queue without it, opencl_manager.cc:55).  While enabled, every kernel
+ * launched through the context is bracketed by CUDA events on the context's stream; totals are
+ * kept per kernel name.  fov_profile_count() synchronises the stream and returns the number of
+ * distinct kernels seen; fov_profile_get() reads entry `index` (name, summed ms, launches). */
+int fov_profile_enable(fov_ctx *ctx, int on);
+int fov_profile_reset(fov_ctx *ctx);
+int fov_profile_count(fov_ctx *ctx);
+int fov_profile_get(fov_ctx *ctx, int index, char *name, size_t name_cap, double *total_ms,
+                    uint64_t *launches);
+
+/* cl::Buffer(context, CL_MEM_READ_WRITE, n) (video_server.cc:224-232). */
+int fov_malloc(fov_ctx *ctx, void **dptr, size_t nbytes);
+int fov_free(fov_ctx *ctx, void *dptr);
+int fov_memset(fov_ctx *ctx, void *dptr, int byte, size_t nbytes);
+/* Blocking copies = cl::copy (video_server.cc:297-299, 342-345). */
+int fov_memcpy_h2d(fov_ctx *ctx, void *dst_dev, const void *src_host, size_t nbytes);
+int fov_memcpy_d2h(fov_ctx *ctx, void *dst_host, const void *src_dev, size_t nbytes);
+/* Stream-ordered copies for pipelined callers (host memory should be pinned). */
+int fov_memcpy_h2d_async(fov_ctx *ctx, void *dst_dev, const void *src_host, size_t nbytes);
+int fov_memcpy_d2h_async(fov_ctx *ctx, void *dst_host, const void *src_dev, size_t nbytes);
+int fov_host_alloc(fov_ctx *ctx, void **hptr, size_t nbytes); /* pinned host memory */
+int fov_host_free(fov_ctx *ctx, void *hptr);
+
+/* ---- SATEncoder (sat_encoder.h:39-40) ------------------------------------------------- */
+
+/* SATEncoder::EncodeFrameGPU (sat_encoder.cc:67-135; copy_image_kernel + scan_rows_kernel +
+ * scan_columns_kernel, sat_encoder_encode_kernels.cl:1-20,44-74).
+ * src: u8[H][src_linesize], pixel stride src_linesize / W (3 or 4), channels 0..2 used.
+ * sat: u32[H][W][3], S[y][x][c] = sum_{y'<=y, x'<=x} I[y'][x'][c] mod 2^32. */
+int fov_sat_encode(fov_ctx *ctx, uint32_t *sat, const uint8_t *src, int width, int height,
+                   int src_linesize);
+/* n independent frames, frame f at base + f*stride (strides in BYTES). One launch set. */
+int fov_sat_encode_batched(fov_ctx *ctx, int n, uint32_t *sat, size_t sat_stride,
+                           const uint8_t *src, size_t src_stride, int width, int height,
+                           int src_linesize);
+
+/* ---- SATDecoder (sat_decoder.h:48-51, 63-66, 78-82) ------------------------------------- */
+
+/* SATDecoder::InitializeGrid (sat_decoder.cc:139-170; create_grid_kernel,
+ * sat_decoder_sample_rect_kernel.cl:243-295).  The reference stores an int16
+ * [(oh+1)][(ow+1)][2] table; its x component depends on the column only and its y
+ * component on the row only, so this library keeps the two 1-D edge tables.  They are
+ * computed on the host at init time (truncating float formulas: bit-exactness requires
+ * the same libm as the oracle) and cached per (ow, oh, W, H). */
+int fov_sat_grid_init(fov_ctx *ctx, int out_width, int out_height, int src_width, int src_height);
+/* Expands the cached tables into the reference's int16[(oh+1)][(ow+1)][2] layout (host memory). */
+int fov_sat_grid_export(fov_ctx *ctx, int16_t *host_grid, int out_width, int out_height,
+                        int src_width, int src_height);
+
+/* SATDecoder::SampleFrameRectGPU (sat_decoder.cc:301-348; sample_rect_kernel,
+ * sat_decoder_sample_rect_kernel.cl:138-241).  `src_width/src_height` are the reference's
+ * codec_ctx->width/height.  out: uchar4[oh][out_linesize/4]; only bytes 0..2 of a pixel
+ * are written, and only when its box touches the frame - other bytes keep their contents.
+ * The grid is built lazily when absent (sat_decoder.cc:312-317). */
+int fov_sat_sample_rect(fov_ctx *ctx, uint8_t *out, int out_width, int out_height,
+                        int out_linesize, const uint32_t *sat, int src_width, int src_height,
+                        float center_x, float center_y);
+/* gaze_xy: HOST array of 2*n floats (x0,y0,x1,y1,...). */
+int fov_sat_sample_rect_batched(fov_ctx *ctx, int n, uint8_t *out, size_t out_stride,
+                                int out_width, int out_height, int out_linesize,
+                                const uint32_t *sat, size_t sat_stride, int src_width,
+                                int src_height, const float *gaze_xy);
+
+/* SATDecoder::InterpolateFrameRectGPU (sat_decoder.cc:887-927; interpolate_rect_kernel,
+ * sat_decoder_interpolate_kernel.cl:1-152).  Inverse log-rectilinear warp + bilinear.
+ * As in the reference, both buffers are addressed as dense 4-byte-pixel arrays and the two
+ * linesize arguments are NOT used (sat_decoder.cc:902-912); all 4 bytes of every target
+ * pixel are written. */
+int fov_sat_interpolate_rect(fov_ctx *ctx, uint8_t *out, int out_width, int out_height,
+                             int out_linesize, const uint8_t *reduced, int red_width,
+                             int red_height, int red_linesize, float center_x, float center_y);
+int fov_sat_interpolate_rect_batched(fov_ctx *ctx, int n, uint8_t *out, size_t out_stride,
+                                     int out_width, int out_height, const uint8_t *reduced,
+                                     size_t red_stride, int red_width, int red_height,
+                                     const float *gaze_xy);
+
+/* SATDecoder::DecodeFrameGPU (sat_decoder.cc:176-210; decode_kernel,
+ * sat_decoder_decode_kernel.cl:1-58): exact SAT -> image inverse (1x1 boxes), clamped to
+ * [0,255]; out pixel stride = out_linesize / W, bytes 0..2 written. */
+int fov_sat_decode(fov_ctx *ctx, uint8_t *out, int out_linesize, const uint32_t *sat, int width,
+                   int height);
+
+/* The offline runner's per-frame sequence (run_satlogrectilinear.cc:926-943:
+ * EncodeFrameGPU -> SampleFrameRectGPU -> InterpolateFrameRectGPU) for n independent frames
+ * with per-frame gaze, enqueued as one batched launch set.  Frame f of every buffer lives at
+ * base + f*stride (strides in BYTES); `sat` is scratch the caller owns (n SATs), `reduced`
+ * receives the foveated buffers (what the server would hand to the video encoder) and
+ * `full_out` the un-warped frames (what the client displays).  Semantics per frame are exactly
+ * those of the three single-frame calls. */
+int fov_sat_foveate_batched(fov_ctx *ctx, int n, uint8_t *full_out, size_t full_stride,
+                            uint8_t *reduced, size_t red_stride, uint32_t *sat, size_t sat_stride,
+                            const uint8_t *src, size_t src_stride, int src_width, int src_height,
+                            int src_linesize, int red_width, int red_height, const float *gaze_xy);
+
+/* ---- ImageSampler (image_sampler.h:57-65, 74-78, 84-91) --------------------------------- */
+
+/* ImageSampler::InitializeGrid (image_sampler.cc:170-202; create_grid_kernel,
+ * image_sampler_sample_rect_kernel.cl:48-88): raw log-rect deltas, kept as two 1-D tables. */
+int fov_img_grid_init(fov_ctx *ctx, int out_width, int out_height, int src_width, int src_height);
+int fov_img_grid_export(fov_ctx *ctx, int16_t *host_grid /* [oh][ow][2] */, int out_width,
+                        int out_height, int src_width, int src_height);
+/* ImageSampler::SampleFrameRectGPU (image_sampler.cc:249-299; sample_rect_kernel, :1-46). */
+int fov_img_sample_rect(fov_ctx *ctx, uint8_t *out, int out_width, int out_height,
+                        int out_linesize, const uint8_t *src, int src_width, int src_height,
+                        int src_linesize, float center_x, float center_y);
+
+/* ImageSampler::InitializeLogpolarGrid (image_sampler.cc:204-247; create_logpolar_grid_kernel,
+ * image_sampler_sample_logpolar_kernel.cl:5-39): (int)(exp(10 i/ow) * (cos,sin)(2 pi j/oh)).
+ * Kept as radius[ow], cos[oh], sin[oh] float tables; the product is formed on the device. */
+int fov_img_logpolar_grid_init(fov_ctx *ctx, int out_width, int out_height, int src_width,
+                               int src_height);
+int fov_img_logpolar_grid_export(fov_ctx *ctx, int16_t *host_grid /* [oh][ow][2] */, int out_width,
+                                 int out_height);
+/* ImageSampler::SampleFrameLogPolarGPU (image_sampler.cc:577-621; sample_logpolar_kernel, :41-86). */
+int fov_img_sample_logpolar(fov_ctx *ctx, uint8_t *out, int out_width, int out_height,
+                            int out_linesize, const uint8_t *src, int src_width, int src_height,
+                            int src_linesize, float center_x, float center_y);
+/* ImageSampler::InterpolateFrameLogPolarGPU (image_sampler.cc:780-818;
+ * interpolate_logpolar_kernel, image_sampler_interpolate_kernel.cl:1-81); linesizes unused. */
+int fov_img_interpolate_logpolar(fov_ctx *ctx, uint8_t *out, int out_width, int out_height,
+                                 int out_linesize, const uint8_t *reduced, int red_width,
+                                 int red_height, int red_linesize, float center_x, float center_y);
+/* ImageSampler::ApplyLogPolarGaussianBlur (image_sampler.cc:820-857;
+ * logpolar_gaussian_blur_kernel, image_sampler_sample_logpolar_kernel.cl:88-142). */
+int fov_img_logpolar_blur(fov_ctx *ctx, uint8_t *out, int width, int height, int linesize,
+                          const uint8_t *src);
+
+/* ---- parameters.h semantics ------------------------------------------------------------ */
+
+/* REDUCED_BUFFER_WIDTH/HEIGHT (parameters.h:8-9) for 1920x1080, and the runner's general rule
+ * 16*ceil(dim/1.8/16) (run_satlogrectilinear.cc:113-114). */
+int fov_reduced_dim(int full_dim);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FOV360_H_ */

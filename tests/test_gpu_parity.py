@@ -1,0 +1,320 @@
+"""GPU parity tests: the CUDA path, called through the C ABI (ctypes -> libfov360.so), against the
+oracle on identical seeded inputs and against the golden fixtures generated from the reference.
+
+Tolerances: SAT, grids, sample_rect, decode, ImageSampler gathers - BIT-EXACT.
+interpolate_rect, blur - <= 1 LSB per channel (BASELINE.json north_star); in practice they are
+bit-exact too and the tests report the mismatch count.  interpolate_logpolar - <= 1 LSB on
+>= 99.9 % of pixels (index rounding at round()/floor() boundaries)."""
+import numpy as np
+import pytest
+
+import _oracle as O
+
+pytestmark = pytest.mark.gpu
+
+GAZES = [(0.5, 0.5), (0.65, 0.75), (0.02, 0.3), (0.98, 0.9), (0.0, 0.0), (1.0, 1.0), (0.0, 1.0),
+         (0.25, 0.999), (0.5001, 0.0)]
+
+
+def ab(oh, ow):
+    return np.full((oh, ow, 4), 0xAB, np.uint8)
+
+
+def max_lsb(a, b):
+    return int(np.abs(a.astype(np.int16) - b.astype(np.int16)).max())
+
+
+class Dev:
+    """Call-sequence helper written like the reference's call sites (video_server.cc:296-345)."""
+
+    def __init__(self, fov, mgr):
+        self.fov, self.m = fov, mgr
+        self.enc, self.dec, self.img = fov.SATEncoder(mgr), fov.SATDecoder(mgr), fov.ImageSampler(mgr)
+
+    def sat(self, frame):
+        H, W, bpp = frame.shape
+        src = self.m.upload(frame)
+        sat = self.m.Buffer(W * H * 12)
+        self.enc.EncodeFrameGPU(sat, src, W, H, W * bpp)
+        out = self.m.copy_to_host(np.empty((H, W, 3), np.uint32), sat)
+        return out, sat
+
+    def sample(self, sat_buf, W, H, ow, oh, cx, cy, prefill=0xAB, linesize=None):
+        linesize = linesize or 4 * ow
+        host = np.full((oh, linesize // 4, 4), prefill, np.uint8)
+        red = self.m.upload(host)
+        self.dec.SampleFrameRectGPU(red, ow, oh, linesize, sat_buf, W, H, cx, cy)
+        return self.m.copy_to_host(host, red), red
+
+    def interpolate(self, red_host, W, H, cx, cy):
+        oh, ow, _ = red_host.shape
+        red = self.m.upload(red_host)
+        full = self.m.upload(np.full((H, W, 4), 0xCD, np.uint8))
+        self.dec.InterpolateFrameRectGPU(full, W, H, 4 * W, red, ow, oh, 4 * ow, cx, cy)
+        return self.m.copy_to_host(np.empty((H, W, 4), np.uint8), full)
+
+
+@pytest.fixture(scope="module")
+def dev(fov, mgr):
+    return Dev(fov, mgr)
+
+
+# ---------------------------------------------------------------------------------- golden ----
+def test_small_golden_vectors(dev, small):
+    W, H, ow, oh = 96, 64, 64, 48
+    sat, sat_buf = dev.sat(small["frame"])
+    assert np.array_equal(sat, small["sat"])
+    assert np.array_equal(dev.dec.ExportGrid(ow, oh, W, H), small["sat_grid"])
+    assert np.array_equal(dev.img.ExportGrid(ow, oh, W, H), small["img_grid"])
+    assert np.array_equal(dev.img.ExportLogpolarGrid(ow, oh), small["lp_grid"])
+    dec = dev.m.upload(np.zeros((H, W, 4), np.uint8))
+    dev.dec.DecodeFrameGPU(dec, 4 * W, sat_buf, W, H)
+    assert np.array_equal(dev.m.copy_to_host(np.empty((H, W, 4), np.uint8), dec), small["decode"])
+    src = dev.m.upload(small["frame"])
+    for k, (cx, cy) in enumerate(small["gazes"]):
+        cx, cy = float(cx), float(cy)
+        red, _ = dev.sample(sat_buf, W, H, ow, oh, cx, cy)
+        assert np.array_equal(red, small["reduced_%d" % k]), k
+        full = dev.interpolate(small["reduced_%d" % k], W, H, cx, cy)
+        assert max_lsb(full[..., :3], small["interp_%d" % k][..., :3]) <= 1
+        out = dev.m.upload(ab(oh, ow))
+        dev.img.SampleFrameLogPolarGPU(out, ow, oh, 4 * ow, src, W, H, 4 * W, cx, cy)
+        lp = dev.m.copy_to_host(ab(oh, ow), out)
+        assert np.array_equal(lp, small["logpolar_%d" % k])
+        out = dev.m.upload(ab(oh, ow))
+        dev.img.SampleFrameRectGPU(out, ow, oh, 4 * ow, src, W, H, 4 * W, cx, cy)
+        assert np.array_equal(dev.m.copy_to_host(ab(oh, ow), out), small["rect_%d" % k])
+        bl = dev.m.upload(ab(oh, ow))
+        dev.img.ApplyLogPolarGaussianBlur(bl, ow, oh, 4 * ow, dev.m.upload(lp))
+        assert max_lsb(dev.m.copy_to_host(ab(oh, ow), bl)[..., :3],
+                       small["blur_%d" % k][..., :3]) <= 1
+        it = dev.m.upload(np.zeros((H, W, 4), np.uint8))
+        dev.img.InterpolateFrameLogPolarGPU(it, W, H, 4 * W, dev.m.upload(lp), ow, oh, 4 * ow, cx, cy)
+        got = dev.m.copy_to_host(np.empty((H, W, 4), np.uint8), it)
+        diff = np.abs(got[..., :3].astype(np.int16) -
+                      small["interp_logpolar_%d" % k][..., :3].astype(np.int16)).max(axis=2)
+        assert (diff > 1).mean() <= 1e-3, (k, int((diff > 1).sum()))
+
+
+@pytest.mark.parametrize("idx", [0, 1, 2])
+def test_golden_hashes_sat_path(dev, golden, idx):
+    c = golden["sat"][idx]
+    W, H, ow, oh = c["W"], c["H"], c["ow"], c["oh"]
+    frame = O.lcg_frame(W, H, c["seed"])
+    sat, sat_buf = dev.sat(frame)
+    assert [int(v) for v in sat[-1, -1]] == c["sat_last"]
+    assert O.fnv1a64(sat) == c["sat"]
+    assert O.fnv1a64(dev.dec.ExportGrid(ow, oh, W, H)) == c["grid"]
+    for g in c["gaze"]:
+        red, _ = dev.sample(sat_buf, W, H, ow, oh, g["cx"], g["cy"], prefill=0)
+        assert O.fnv1a64(red) == g["reduced_zero"], g
+        red_ab, _ = dev.sample(sat_buf, W, H, ow, oh, g["cx"], g["cy"], prefill=0xAB)
+        assert O.fnv1a64(red_ab) == g["reduced_ab"], g
+        full = dev.interpolate(red, W, H, g["cx"], g["cy"])
+        if O.fnv1a64(full) != g["interp"]:  # tolerance path: <= 1 LSB vs the oracle
+            want = O.port().sat_interpolate_rect(red, W, H, g["cx"], g["cy"])
+            assert max_lsb(full[..., :3], want[..., :3]) <= 1
+
+
+def test_golden_grid_hashes(dev, golden):
+    for g in golden["grids"]:
+        assert O.fnv1a64(dev.dec.ExportGrid(g["ow"], g["oh"], g["W"], g["H"])) == g["sat_grid"], g
+        assert O.fnv1a64(dev.img.ExportGrid(g["ow"], g["oh"], g["W"], g["H"])) == g["img_grid"], g
+
+
+# ------------------------------------------------------------------------------ SAT encode ----
+@pytest.mark.parametrize("W,H", [(1920, 1080), (3840, 1920), (640, 360), (128, 8), (132, 9),
+                                 (4, 1), (1, 1), (7, 5), (1001, 37), (516, 300)])
+def test_sat_bit_exact_vs_oracle(dev, oracle, W, H):
+    frame = O.lcg_frame(W, H, 1000 + W)
+    sat, _ = dev.sat(frame)
+    assert np.array_equal(sat, oracle.sat_encode(frame))
+
+
+def test_sat_rgb24_and_padded_linesize(dev, oracle):
+    W, H = 333, 41
+    rgb0 = O.lcg_frame(W, H, 8)
+    want = oracle.sat_encode(rgb0)
+    rgb = np.ascontiguousarray(rgb0[..., :3])  # 3-byte pixels: linesize / W == 3
+    src = dev.m.upload(rgb)
+    sat = dev.m.Buffer(W * H * 12)
+    dev.enc.EncodeFrameGPU(sat, src, W, H, 3 * W)
+    assert np.array_equal(dev.m.copy_to_host(np.empty((H, W, 3), np.uint32), sat), want)
+
+
+def test_sat_8k_wraparound_and_checksums(dev):
+    """Full-size properties at 7680x3840: all-255 wraps mod 2^32; closed forms for every entry."""
+    W, H = 7680, 3840
+    frame = np.zeros((H, W, 4), np.uint8)
+    frame[..., :3] = 255
+    sat, sat_buf = dev.sat(frame)
+    yy = np.arange(1, H + 1, dtype=np.uint64)[:, None]
+    xx = np.arange(1, W + 1, dtype=np.uint64)[None, :]
+    want = ((yy * xx * 255) % (1 << 32)).astype(np.uint32)
+    for c in range(3):
+        assert np.array_equal(sat[..., c], want)
+    # exact decode of the wrapped SAT gives the frame back
+    dec = dev.m.Buffer(W * H * 4)
+    dev.m.memset(dec, 0, W * H * 4)
+    dev.dec.DecodeFrameGPU(dec, 4 * W, sat_buf, W, H)
+    assert np.array_equal(dev.m.copy_to_host(np.empty((H, W, 4), np.uint8), dec), frame)
+
+
+def test_sat_8k_random_vs_numpy(dev):
+    W, H = 7680, 3840
+    frame = O.lcg_frame(W, H, 31337)
+    sat, _ = dev.sat(frame)
+    want = frame[..., :3].astype(np.uint32)
+    np.cumsum(want, axis=1, out=want)
+    np.cumsum(want, axis=0, out=want)
+    assert np.array_equal(sat, want)
+
+
+def test_decode_roundtrip_identity(dev):
+    for (W, H) in [(1920, 1080), (250, 130)]:
+        frame = O.lcg_frame(W, H, 5)
+        _, sat_buf = dev.sat(frame)
+        out = dev.m.upload(np.zeros((H, W, 4), np.uint8))
+        dev.dec.DecodeFrameGPU(out, 4 * W, sat_buf, W, H)
+        assert np.array_equal(dev.m.copy_to_host(np.empty((H, W, 4), np.uint8), out), frame)
+
+
+def test_batched_encode_matches_single(dev, oracle):
+    W, H, n = 640, 360, 5
+    frames = np.stack([O.lcg_frame(W, H, 50 + f) for f in range(n)])
+    src = dev.m.upload(frames)
+    sat = dev.m.Buffer(n * W * H * 12)
+    dev.enc.EncodeFramesGPU(n, sat, W * H * 12, src, W * H * 4, W, H, 4 * W)
+    got = dev.m.copy_to_host(np.empty((n, H, W, 3), np.uint32), sat)
+    for f in range(n):
+        assert np.array_equal(got[f], oracle.sat_encode(frames[f])), f
+
+
+# ----------------------------------------------------------------------- sample / interpolate ----
+@pytest.mark.parametrize("W,H,ow,oh", [(1920, 1080, 1072, 608), (640, 360, 368, 208),
+                                       (1000, 500, 300, 200), (333, 211, 100, 77)])
+def test_sample_and_interpolate_vs_oracle(dev, oracle, W, H, ow, oh):
+    frame = O.smooth_frame(W, H, seed=W)
+    sat, sat_buf = dev.sat(frame)
+    grid = oracle.sat_create_grid(ow, oh, W, H)
+    assert np.array_equal(dev.dec.ExportGrid(ow, oh, W, H), grid)
+    worst = 0
+    for cx, cy in GAZES:
+        red, _ = dev.sample(sat_buf, W, H, ow, oh, cx, cy)
+        want = oracle.sat_sample_rect(sat, ow, oh, cx, cy, grid=grid, out=ab(oh, ow))
+        assert np.array_equal(red, want), (cx, cy)  # includes untouched 0xAB pixels and alpha
+        full = dev.interpolate(want, W, H, cx, cy)
+        wfull = oracle.sat_interpolate_rect(want, W, H, cx, cy)
+        worst = max(worst, max_lsb(full[..., :3], wfull[..., :3]))
+        assert worst <= 1, (cx, cy, int((full != wfull).sum()))
+
+
+def test_sample_padded_target_linesize(dev, oracle):
+    W, H, ow, oh = 640, 360, 368, 208
+    frame = O.lcg_frame(W, H, 4)
+    sat, sat_buf = dev.sat(frame)
+    linesize = 4 * (ow + 24)
+    got, _ = dev.sample(sat_buf, W, H, ow, oh, 0.4, 0.6, linesize=linesize)
+    want = oracle.sat_sample_rect(sat, ow, oh, 0.4, 0.6, out=np.full((oh, ow + 24, 4), 0xAB, np.uint8))
+    assert np.array_equal(got, want)
+
+
+def test_gaze_sweep_9x9_4k(dev, oracle):
+    """configs[1]: 3840x1920 at varying gaze points - 9x9 lattice, sample bit-exact."""
+    W, H, ow, oh = 3840, 1920, 2144, 1072
+    frame = O.smooth_frame(W, H, seed=11)
+    sat, sat_buf = dev.sat(frame)
+    grid = oracle.sat_create_grid(ow, oh, W, H)
+    lattice = [(i / 8.0, j / 8.0) for j in range(9) for i in range(9)]
+    for k, (cx, cy) in enumerate(lattice):
+        red, _ = dev.sample(sat_buf, W, H, ow, oh, cx, cy)
+        want = oracle.sat_sample_rect(sat, ow, oh, cx, cy, grid=grid, out=ab(oh, ow))
+        assert np.array_equal(red, want), (cx, cy)
+        if k % 10 == 0:
+            full = dev.interpolate(want, W, H, cx, cy)
+            assert max_lsb(full[..., :3], oracle.sat_interpolate_rect(want, W, H, cx, cy)[..., :3]) <= 1
+
+
+def test_roundtrip_identity_near_gaze_8k(dev):
+    """Size-independent property at BASELINE's full size: around the gaze the encode -> sample ->
+    interpolate round trip is the identity."""
+    W, H = 7680, 3840
+    ow, oh = 4272, 2144
+    frame = O.lcg_frame(W, H, 2024)
+    _, sat_buf = dev.sat(frame)
+    for cx, cy in [(0.5, 0.5), (0.65, 0.75), (0.1, 0.2)]:
+        red, _ = dev.sample(sat_buf, W, H, ow, oh, cx, cy, prefill=0)
+        full = dev.interpolate(red, W, H, cx, cy)
+        px, py = int(np.float32(cx) * np.float32(W)), int(np.float32(cy) * np.float32(H))
+        win = (slice(py - 20, py + 21), slice(px - 20, px + 21), slice(0, 3))
+        assert np.array_equal(full[win], frame[win]), (cx, cy)
+
+
+def test_batched_pipeline_matches_single_calls(dev, fov, oracle):
+    """configs[2] shape: batched frames with per-frame gaze through fov_sat_foveate_batched."""
+    W, H, n = 1280, 720, 6
+    ow, oh = fov.reduced_dim(W), fov.reduced_dim(H)
+    rng = np.random.default_rng(1)
+    gaze = rng.random((n, 2)).astype(np.float32)
+    frames = np.stack([O.smooth_frame(W, H, seed=f) for f in range(n)])
+    src = dev.m.upload(frames)
+    sat = dev.m.Buffer(n * W * H * 12)
+    red = dev.m.upload(np.zeros((n, oh, ow, 4), np.uint8))
+    full = dev.m.Buffer(n * W * H * 4)
+    fov.FoveateFramesGPU(dev.m, n, full, W * H * 4, red, ow * oh * 4, sat, W * H * 12, src,
+                         W * H * 4, W, H, 4 * W, ow, oh, gaze)
+    got_red = dev.m.copy_to_host(np.empty((n, oh, ow, 4), np.uint8), red)
+    got_full = dev.m.copy_to_host(np.empty((n, H, W, 4), np.uint8), full)
+    for f in range(n):
+        s = oracle.sat_encode(frames[f])
+        r = oracle.sat_sample_rect(s, ow, oh, float(gaze[f, 0]), float(gaze[f, 1]))
+        assert np.array_equal(got_red[f], r), f
+        w = oracle.sat_interpolate_rect(r, W, H, float(gaze[f, 0]), float(gaze[f, 1]))
+        assert max_lsb(got_full[f][..., :3], w[..., :3]) <= 1, f
+
+
+# --------------------------------------------------------------------------- ImageSampler ----
+@pytest.mark.parametrize("W,H,ow,oh", [(1920, 1080, 1072, 608), (640, 360, 368, 208)])
+def test_image_sampler_vs_oracle(dev, oracle, W, H, ow, oh):
+    frame = O.smooth_frame(W, H, seed=3)
+    src = dev.m.upload(frame)
+    assert np.array_equal(dev.img.ExportGrid(ow, oh, W, H), oracle.img_create_grid(ow, oh, W, H))
+    assert np.array_equal(dev.img.ExportLogpolarGrid(ow, oh),
+                          oracle.img_create_logpolar_grid(ow, oh, W, H))
+    for cx, cy in GAZES[:6]:
+        out = dev.m.upload(ab(oh, ow))
+        dev.img.SampleFrameRectGPU(out, ow, oh, 4 * ow, src, W, H, 4 * W, cx, cy)
+        assert np.array_equal(dev.m.copy_to_host(ab(oh, ow), out),
+                              oracle.img_sample_rect(frame, ow, oh, cx, cy, out=ab(oh, ow)))
+        out = dev.m.upload(ab(oh, ow))
+        dev.img.SampleFrameLogPolarGPU(out, ow, oh, 4 * ow, src, W, H, 4 * W, cx, cy)
+        lp = dev.m.copy_to_host(ab(oh, ow), out)
+        assert np.array_equal(lp, oracle.img_sample_logpolar(frame, ow, oh, cx, cy, out=ab(oh, ow)))
+        bl = dev.m.upload(ab(oh, ow))
+        dev.img.ApplyLogPolarGaussianBlur(bl, ow, oh, 4 * ow, dev.m.upload(lp))
+        assert max_lsb(dev.m.copy_to_host(ab(oh, ow), bl)[..., :3],
+                       oracle.img_logpolar_blur(lp)[..., :3]) <= 1
+        it = dev.m.upload(np.zeros((H, W, 4), np.uint8))
+        dev.img.InterpolateFrameLogPolarGPU(it, W, H, 4 * W, dev.m.upload(lp), ow, oh, 4 * ow, cx, cy)
+        got = dev.m.copy_to_host(np.empty((H, W, 4), np.uint8), it)
+        want = oracle.img_interpolate_logpolar(lp, W, H, cx, cy)
+        diff = np.abs(got[..., :3].astype(np.int16) - want[..., :3].astype(np.int16)).max(axis=2)
+        bad = int((diff > 1).sum())
+        assert bad <= 1e-3 * W * H, (cx, cy, bad)
+
+
+# ------------------------------------------------------------------------------- plumbing ----
+def test_invalid_arguments_are_rejected(dev, fov):
+    buf = dev.m.Buffer(1024)
+    with pytest.raises(fov.FovError):
+        dev.enc.EncodeFrameGPU(buf, buf, 0, 8, 32)
+    with pytest.raises(fov.FovError):
+        dev.enc.EncodeFrameGPU(buf, buf, 8, 8, 8)  # linesize < 3 * W
+    with pytest.raises(fov.FovError):
+        dev.dec.SampleFrameRectGPU(buf, 8, 8, 16, buf, 64, 64, 0.5, 0.5)  # linesize < 4 * ow
+
+
+def test_launch_counter_counts_kernels(dev):
+    before = dev.m.launch_count
+    dev.sat(O.lcg_frame(64, 64, 1))
+    assert dev.m.launch_count - before >= 1

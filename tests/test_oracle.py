@@ -1,0 +1,142 @@
+"""CPU tests of the oracle (oracle/fov_oracle.c): pinned to the golden fixtures generated from the
+reference's own kernel sources, to the reference library itself when it is present, and to the
+invariants SURVEY.md section 4 derives from the reference code."""
+import numpy as np
+import pytest
+
+import _oracle as O
+
+GAZES = [(0.5, 0.5), (0.65, 0.75), (0.02, 0.3), (0.98, 0.9), (0.0, 0.0), (1.0, 1.0), (0.0, 1.0)]
+
+
+def test_small_vectors_match_reference_outputs(oracle, small):
+    W, H, ow, oh = 96, 64, 64, 48
+    frame = small["frame"]
+    sat = oracle.sat_encode(frame)
+    assert np.array_equal(sat, small["sat"])
+    assert np.array_equal(oracle.sat_create_grid(ow, oh, W, H), small["sat_grid"])
+    assert np.array_equal(oracle.sat_decode(sat), small["decode"])
+    assert np.array_equal(oracle.img_create_grid(ow, oh, W, H), small["img_grid"])
+    assert np.array_equal(oracle.img_create_logpolar_grid(ow, oh, W, H), small["lp_grid"])
+    for k, (cx, cy) in enumerate(small["gazes"]):
+        cx, cy = float(cx), float(cy)
+        ab = lambda: np.full((oh, ow, 4), 0xAB, np.uint8)  # noqa: E731
+        red = oracle.sat_sample_rect(sat, ow, oh, cx, cy, out=ab())
+        assert np.array_equal(red, small["reduced_%d" % k]), k
+        assert np.array_equal(oracle.sat_interpolate_rect(red, W, H, cx, cy), small["interp_%d" % k])
+        lp = oracle.img_sample_logpolar(frame, ow, oh, cx, cy, out=ab())
+        assert np.array_equal(lp, small["logpolar_%d" % k])
+        assert np.array_equal(oracle.img_sample_rect(frame, ow, oh, cx, cy, out=ab()),
+                              small["rect_%d" % k])
+        assert np.array_equal(oracle.img_logpolar_blur(lp), small["blur_%d" % k])
+        assert np.array_equal(oracle.img_interpolate_logpolar(lp, W, H, cx, cy),
+                              small["interp_logpolar_%d" % k])
+
+
+@pytest.mark.parametrize("idx", [0, 2])
+def test_sat_path_hashes(oracle, golden, idx):
+    c = golden["sat"][idx]
+    W, H, ow, oh = c["W"], c["H"], c["ow"], c["oh"]
+    frame = O.lcg_frame(W, H, c["seed"])
+    assert O.fnv1a64(frame) == c["frame"]
+    sat = oracle.sat_encode(frame)
+    assert [int(v) for v in sat[-1, -1]] == c["sat_last"]
+    assert O.fnv1a64(sat) == c["sat"]
+    grid = oracle.sat_create_grid(ow, oh, W, H)
+    assert O.fnv1a64(grid) == c["grid"]
+    for g in c["gaze"]:
+        red = oracle.sat_sample_rect(sat, ow, oh, g["cx"], g["cy"], grid=grid)
+        assert O.fnv1a64(red) == g["reduced_zero"]
+        assert [int(v) for v in red[oh // 2, ow // 2, :3]] == g["centre_px"]
+        assert O.fnv1a64(oracle.sat_interpolate_rect(red, W, H, g["cx"], g["cy"])) == g["interp"]
+
+
+def test_logpolar_path_hashes(oracle, golden):
+    c = golden["logpolar"][1]
+    W, H, ow, oh = c["W"], c["H"], c["ow"], c["oh"]
+    frame = O.lcg_frame(W, H, c["seed"])
+    assert O.fnv1a64(oracle.img_create_logpolar_grid(ow, oh, W, H)) == c["lp_grid"]
+    assert O.fnv1a64(oracle.img_create_grid(ow, oh, W, H)) == c["rect_grid"]
+    for g in c["gaze"]:
+        lp = oracle.img_sample_logpolar(frame, ow, oh, g["cx"], g["cy"])
+        assert O.fnv1a64(lp) == g["logpolar"]
+        assert O.fnv1a64(oracle.img_sample_rect(frame, ow, oh, g["cx"], g["cy"])) == g["rect"]
+        assert O.fnv1a64(oracle.img_logpolar_blur(lp)) == g["blur"]
+        assert O.fnv1a64(oracle.img_interpolate_logpolar(lp, W, H, g["cx"], g["cy"])) == \
+            g["interp_logpolar"]
+
+
+def test_grid_hashes_all_resolutions(oracle, golden):
+    for g in golden["grids"]:
+        grid = oracle.sat_create_grid(g["ow"], g["oh"], g["W"], g["H"])
+        assert O.fnv1a64(grid) == g["sat_grid"], g
+        assert [int(v) for v in grid[0, :4, 0]] == g["x_head"]
+        assert int(grid[-1, 0, 1]) == g["y_last"]
+        assert O.fnv1a64(oracle.img_create_grid(g["ow"], g["oh"], g["W"], g["H"])) == g["img_grid"]
+        # separability: x depends on the column only, y on the row only
+        assert (grid[:, :, 0] == grid[0:1, :, 0]).all() and (grid[:, :, 1] == grid[:, 0:1, 1]).all()
+
+
+@pytest.mark.skipif(not O.ref_available(), reason="reference library not built / not present")
+def test_port_matches_reference_library_bit_for_bit():
+    port, ref = O.Oracle("port"), O.Oracle("ref")
+    W, H = 400, 232
+    ow, oh = O.reduced_size(W), O.reduced_size(H)
+    for frame in (O.lcg_frame(W, H, 5), O.smooth_frame(W, H), np.full((H, W, 4), 255, np.uint8)):
+        sp, sr = port.sat_encode(frame), ref.sat_encode(frame)
+        assert np.array_equal(sp, sr)
+        assert np.array_equal(port.sat_decode(sp), ref.sat_decode(sr))
+        for cx, cy in GAZES:
+            a = port.sat_sample_rect(sp, ow, oh, cx, cy)
+            b = ref.sat_sample_rect(sr, ow, oh, cx, cy)
+            assert np.array_equal(a, b)
+            assert np.array_equal(port.sat_interpolate_rect(a, W, H, cx, cy),
+                                  ref.sat_interpolate_rect(b, W, H, cx, cy))
+            la = port.img_sample_logpolar(frame, ow, oh, cx, cy)
+            lb = ref.img_sample_logpolar(frame, ow, oh, cx, cy)
+            assert np.array_equal(la, lb)
+            assert np.array_equal(port.img_sample_rect(frame, ow, oh, cx, cy),
+                                  ref.img_sample_rect(frame, ow, oh, cx, cy))
+            assert np.array_equal(port.img_logpolar_blur(la), ref.img_logpolar_blur(lb))
+            assert np.array_equal(port.img_interpolate_logpolar(la, W, H, cx, cy),
+                                  ref.img_interpolate_logpolar(lb, W, H, cx, cy))
+
+
+def test_rgb24_source_stride(oracle):
+    """bytes_per_pixel = linesize / width (sat_encoder_encode_kernels.cl:9): 3-byte pixels."""
+    W, H = 50, 20
+    rgb0 = O.lcg_frame(W, H, 3)
+    sat4 = oracle.sat_encode(rgb0)
+    sat3 = oracle.sat_encode(np.ascontiguousarray(rgb0[..., :3]))
+    assert np.array_equal(sat3, sat4)
+
+
+def test_invariants(oracle):
+    W, H = 640, 360
+    ow, oh = O.reduced_size(W), O.reduced_size(H)
+    frame = O.lcg_frame(W, H, 777)
+    sat = oracle.sat_encode(frame)
+    # decode(SAT(img)) == img; last element == channel sums mod 2^32
+    assert np.array_equal(oracle.sat_decode(sat)[..., :3], frame[..., :3])
+    sums = frame[..., :3].reshape(-1, 3).astype(np.uint64).sum(axis=0) % (1 << 32)
+    assert [int(v) for v in sat[-1, -1]] == [int(v) for v in sums]
+    # around the gaze the round trip is the identity
+    for cx, cy in [(0.5, 0.5), (0.65, 0.75)]:
+        red = oracle.sat_sample_rect(sat, ow, oh, cx, cy)
+        full = oracle.sat_interpolate_rect(red, W, H, cx, cy)
+        px, py = int(np.float32(cx) * np.float32(W)), int(np.float32(cy) * np.float32(H))
+        win = (slice(py - 12, py + 13), slice(px - 12, px + 13), slice(0, 3))
+        assert np.array_equal(full[win], frame[win])
+
+
+def test_wraparound_all_white(oracle):
+    """u32 sums wrap mod 2^32 and box differences stay exact (sat_encoder_encode_kernels.cl:47,63)."""
+    W, H = 4200, 4100  # 4200*4100*255 = 4.39e9 > 2^32
+    frame = np.zeros((H, W, 4), np.uint8)
+    frame[..., :3] = 255
+    sat = oracle.sat_encode(frame)
+    assert int(sat[-1, -1, 0]) == (W * H * 255) % (1 << 32)
+    ow, oh = 64, 64
+    red = oracle.sat_sample_rect(sat, ow, oh, 0.9, 0.9, out=np.full((oh, ow, 4), 0xAB, np.uint8))
+    written = (red[..., :3] != 0xAB).any(axis=2)
+    assert written.any() and (red[written][:, :3] == 255).all()
