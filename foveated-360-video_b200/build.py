@@ -10,6 +10,7 @@ every operation separately (see the header of that file).
 from __future__ import annotations
 
 import concurrent.futures as cf
+import hashlib
 import os
 import shutil
 import subprocess
@@ -40,6 +41,18 @@ def nvcc_path() -> str:
     raise RuntimeError("nvcc not found: libfov360.so cannot be built (there is no CPU fallback)")
 
 
+MANIFEST = os.path.join(HERE, "libfov360.manifest")
+
+
+def _digest(paths: list[str]) -> str:
+    """Content hash of the build inputs: mtimes do not survive the snapshot to the GPU box."""
+    h = hashlib.sha256(" ".join(NVCC_FLAGS).encode())
+    for p in paths:
+        with open(p, "rb") as fh:
+            h.update(p.rsplit(os.sep, 1)[-1].encode() + b"\0" + fh.read())
+    return h.hexdigest()
+
+
 def _stale(target: str, deps: list[str]) -> bool:
     if not os.path.exists(target):
         return True
@@ -61,19 +74,26 @@ def _compile(nvcc: str, src: str, obj: str, verbose: bool) -> None:
 def build(force: bool = False, verbose: bool = False) -> str:
     """Builds (if stale) and returns the path of libfov360.so."""
     srcs = [os.path.join(CSRC, s) for s in SOURCES]
-    if not force and not _stale(LIB_PATH, srcs + HEADERS + [os.path.abspath(__file__)]):
-        return LIB_PATH
+    digest = _digest(srcs + HEADERS)
+    if not force and os.path.exists(LIB_PATH) and os.path.exists(MANIFEST):
+        with open(MANIFEST) as fh:
+            if fh.read().strip() == digest:
+                return LIB_PATH
     nvcc = nvcc_path()
     os.makedirs(OBJ_DIR, exist_ok=True)
     objs = [os.path.join(OBJ_DIR, os.path.splitext(s)[0] + ".o") for s in SOURCES]
     todo = [(s, o) for s, o in zip(srcs, objs)
             if force or _stale(o, [s] + HEADERS + [os.path.abspath(__file__)])]
+    todo = todo if os.path.exists(MANIFEST) else list(zip(srcs, objs))
     with cf.ThreadPoolExecutor(max_workers=max(1, min(len(todo), os.cpu_count() or 1))) as ex:
         for fut in [ex.submit(_compile, nvcc, s, o, verbose) for s, o in todo]:
             fut.result()
     tmp = LIB_PATH + ".tmp"
     subprocess.check_call([nvcc, *ARCH, "-shared", "-cudart", "static", "-o", tmp, *objs])
     os.replace(tmp, LIB_PATH)
+    with open(MANIFEST + ".tmp", "w") as fh:
+        fh.write(digest + "\n")
+    os.replace(MANIFEST + ".tmp", MANIFEST)
     return LIB_PATH
 
 
