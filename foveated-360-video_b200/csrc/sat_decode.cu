@@ -33,7 +33,16 @@ __device__ __forceinline__ uint32_t udiv_exact(uint32_t num, uint32_t den, float
 }
 
 // ---------------------------------------------------------------------------------------
-// sample_rect: one thread per reduced pixel; 4 SAT corners (12 B each) -> box average.
+// sample_rect: box average from 4 SAT corners per reduced pixel.
+//
+// Neighbouring boxes share corners: the right edge of pixel i is the left edge of pixel i+1 and
+// the bottom edge of row j is the top edge of row j+1 (both come from the same edge-table entry),
+// except where the reference's clamps / seam wrap move one of them (frame borders).  A warp
+// covers 31 pixel columns x kSampleRows rows: every lane gathers only its LEFT corner of the new
+// bottom edge (12 B), takes the right corner from lane+1 by shuffle and reuses the previous
+// bottom edge as its top edge - 3 gathered words per pixel instead of 12.  Lane 31 only supplies
+// the right edge of lane 30.  Wherever a shared coordinate differs from the one the reference
+// would use, the lane falls back to gathering it itself, so results stay bit-exact.
 // ---------------------------------------------------------------------------------------
 struct SampleArgs {
   uint8_t *out;
@@ -43,57 +52,111 @@ struct SampleArgs {
   int ow, oh, o_linesize_px, W, H;
 };
 
+constexpr int kSampleCols = 31;
+constexpr int kSampleRows = 8;
+
+struct Rgb32 {
+  uint32_t r, g, b;
+};
+
+__device__ __forceinline__ Rgb32 ld_sat(const uint32_t *p) {
+  Rgb32 v;
+  v.r = __ldg(p);
+  v.g = __ldg(p + 1);
+  v.b = __ldg(p + 2);
+  return v;
+}
+
+__device__ __forceinline__ Rgb32 shfl_down1(const Rgb32 v) {
+  Rgb32 o;
+  o.r = __shfl_down_sync(0xffffffffu, v.r, 1);
+  o.g = __shfl_down_sync(0xffffffffu, v.g, 1);
+  o.b = __shfl_down_sync(0xffffffffu, v.b, 1);
+  return o;
+}
+
 __global__ void __launch_bounds__(256) sat_sample_rect_kernel(const SampleArgs a,
                                                               const GazeBatch g) {
-  const int i = blockIdx.x * 32 + threadIdx.x;
-  const int j = blockIdx.y * 8 + threadIdx.y;
+  const int lane = threadIdx.x;
+  const int i = blockIdx.x * kSampleCols + lane;
+  const int j0 = (blockIdx.y * 8 + threadIdx.y) * kSampleRows;
   const int f = blockIdx.z;
-  if (i >= a.ow || j >= a.oh) return;
-  const int W = a.W, H = a.H;
+  if (j0 >= a.oh) return;  // warp-uniform
+  const int W = a.W, H = a.H, ow = a.ow, oh = a.oh;
   const int cxp = gaze_px(g.xy[2 * f], W);
   const int cyp = gaze_px(g.xy[2 * f + 1], H);
+  const bool has_px = lane < kSampleCols && i < ow;
 
-  int px = cxp + a.xedge[i + 1];  // grid[j+1][i+1].x  (:168-169)
-  int mx = cxp + a.xedge[i];      // grid[j+1][i].x    (:170-171)
-  int py = cyp + a.yedge[j + 1];  // grid[j+1][i+1].y  (:172-173)
-  int my = cyp + a.yedge[j];      // grid[j][i+1].y    (:174-175)
-  if (px >= W && mx >= W) {       // :181-187
+  // x edges of this lane's pixel (lanes past the last pixel compute harmless in-range values)
+  const int ic = min(i, ow - 1);
+  int px = cxp + a.xedge[ic + 1];  // grid[j+1][i+1].x  (:168-169)
+  int mx = cxp + a.xedge[ic];      // grid[j+1][i].x    (:170-171)
+  if (px >= W && mx >= W) {        // :181-187
     px -= W;
     mx -= W;
   } else if (px < 0 && mx < 0) {
     px += W;
     mx += W;
   }
-  const bool x_in = (px >= 0 && px < W) || (mx >= 0 && mx < W);
-  const bool y_in = (py >= 0 && py < H) || (my >= 0 && my < H);
-  if (!(x_in && y_in)) return;  // :197-200: leave the pixel untouched
-  px = clampi(px, 1, W - 1);    // :201-204
-  py = clampi(py, 1, H - 1);
+  const bool x_in = (px >= 0 && px < W) || (mx >= 0 && mx < W);  // :197-198
+  px = clampi(px, 1, W - 1);                                      // :201, :203
   mx = clampi(mx, 0, px - 1);
-  my = clampi(my, 0, py - 1);
+  // lane+1 gathers its own left corner at mx(lane+1); usable as this lane's right corner iff equal
+  const int mx_next = __shfl_down_sync(0xffffffffu, mx, 1);
+  const bool share = lane < 31 && i + 1 < ow && px == mx_next;
+  const bool own_right = has_px && !share;
 
   const uint32_t *sat =
       reinterpret_cast<const uint32_t *>(reinterpret_cast<const uint8_t *>(a.sat) +
                                          (size_t)f * a.sat_stride);
-  const uint32_t *tl = sat + ((size_t)my * W + mx) * 3;
-  const uint32_t *tr = sat + ((size_t)my * W + px) * 3;
-  const uint32_t *bl = sat + ((size_t)py * W + mx) * 3;
-  const uint32_t *br = sat + ((size_t)py * W + px) * 3;
-  uint32_t s0 = __ldg(br + 0) - __ldg(tr + 0) + __ldg(tl + 0) - __ldg(bl + 0);  // :212-217
-  uint32_t s1 = __ldg(br + 1) - __ldg(tr + 1) + __ldg(tl + 1) - __ldg(bl + 1);
-  uint32_t s2 = __ldg(br + 2) - __ldg(tr + 2) + __ldg(tl + 2) - __ldg(bl + 2);
-  const uint32_t area = (uint32_t)((px - mx) * (py - my));  // :211
-  if (area != 1u) {
-    const float r = __frcp_rn((float)area);
-    s0 = udiv_exact(s0, area, r);
-    s1 = udiv_exact(s1, area, r);
-    s2 = udiv_exact(s2, area, r);
+  uint32_t *orow = reinterpret_cast<uint32_t *>(a.out + (size_t)f * a.out_stride) +
+                   (size_t)j0 * a.o_linesize_px + i;
+
+  int prev_y = -1;
+  Rgb32 pl = {0, 0, 0}, pr = {0, 0, 0};  // previous bottom edge: left / right corner
+  const int j1 = min(j0 + kSampleRows, oh);
+  for (int j = j0; j < j1; ++j, orow += a.o_linesize_px) {
+    int py = cyp + a.yedge[j + 1];  // grid[j+1][i+1].y  (:172-173)
+    int my = cyp + a.yedge[j];      // grid[j][i+1].y    (:174-175)
+    const bool y_in = (py >= 0 && py < H) || (my >= 0 && my < H);  // :199-200
+    if (!y_in) {  // warp-uniform: the whole row keeps its contents
+      prev_y = -1;
+      continue;
+    }
+    py = clampi(py, 1, H - 1);  // :202, :204
+    my = clampi(my, 0, py - 1);
+    Rgb32 tl, tr;
+    if (my == prev_y) {  // warp-uniform
+      tl = pl;
+      tr = pr;
+    } else {
+      const uint32_t *row = sat + (size_t)my * W * 3;
+      tl = ld_sat(row + (size_t)mx * 3);
+      tr = shfl_down1(tl);
+      if (own_right) tr = ld_sat(row + (size_t)px * 3);
+    }
+    const uint32_t *row = sat + (size_t)py * W * 3;
+    const Rgb32 bl = ld_sat(row + (size_t)mx * 3);
+    Rgb32 br = shfl_down1(bl);
+    if (own_right) br = ld_sat(row + (size_t)px * 3);
+    pl = bl;
+    pr = br;
+    prev_y = py;
+    if (has_px && x_in) {
+      uint32_t s0 = br.r - tr.r + tl.r - bl.r;  // :212-217
+      uint32_t s1 = br.g - tr.g + tl.g - bl.g;
+      uint32_t s2 = br.b - tr.b + tl.b - bl.b;
+      const uint32_t area = (uint32_t)((px - mx) * (py - my));  // :211
+      if (area != 1u) {
+        const float rcp = __frcp_rn((float)area);
+        s0 = udiv_exact(s0, area, rcp);
+        s1 = udiv_exact(s1, area, rcp);
+        s2 = udiv_exact(s2, area, rcp);
+      }
+      // `.xyz =` store: byte 3 of the uchar4 keeps its previous value (:212).
+      *orow = (*orow & 0xff000000u) | (s0 & 0xffu) | ((s1 & 0xffu) << 8) | ((s2 & 0xffu) << 16);
+    }
   }
-  // `.xyz =` store: byte 3 of the uchar4 keeps its previous value (:212).
-  uint32_t *o = reinterpret_cast<uint32_t *>(a.out + (size_t)f * a.out_stride) +
-                (size_t)j * a.o_linesize_px + i;
-  const uint32_t old = *o;
-  *o = (old & 0xff000000u) | (s0 & 0xffu) | ((s1 & 0xffu) << 8) | ((s2 & 0xffu) << 16);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -143,80 +206,234 @@ __device__ __forceinline__ InterpEntry load_entry(const InterpEntry *p) {
   return e;
 }
 
+// u8 -> float without the conversion pipe: splice the byte into the mantissa of 2^23 (one PRMT)
+// and subtract 2^23 (one FADD); exact for 0..255.
+template <int C>
+__device__ __forceinline__ float byte_to_float(uint32_t v) {
+  return __fsub_rn(__uint_as_float(__byte_perm(v, 0x4B000000u, 0x7440u | C)), 8388608.0f);
+}
+
 // mix(a, b, t) = a + (b - a) * t with every operation rounded separately (no FMA), matching
 // the oracle's scalar float arithmetic (:143-150).
 __device__ __forceinline__ float mix_rn(float a, float b, float t) {
+#ifdef FOV360_FUSED_LERP
+  return __fmaf_rn(__fsub_rn(b, a), t, a);  // <= 1 LSB after truncation, not bit-exact
+#else
   return __fadd_rn(a, __fmul_rn(__fsub_rn(b, a), t));
+#endif
 }
 
-__device__ __forceinline__ uint32_t lerp_pixel(uint32_t tl, uint32_t tr, uint32_t bl, uint32_t br,
-                                               float tx, float ty) {
-  uint32_t outp = 0;
-#pragma unroll
-  for (int c = 0; c < 3; ++c) {
-    const float ftl = (float)((tl >> (8 * c)) & 0xffu);
-    const float ftr = (float)((tr >> (8 * c)) & 0xffu);
-    const float fbl = (float)((bl >> (8 * c)) & 0xffu);
-    const float fbr = (float)((br >> (8 * c)) & 0xffu);
-    const float l = mix_rn(ftl, fbl, ty);
-    const float r = mix_rn(ftr, fbr, ty);
-    const int v = __float2int_rz(mix_rn(l, r, tx));
-    outp |= ((uint32_t)v & 0xffu) << (8 * c);
-  }
-  return outp;  // byte 3 = 0 (convert_uchar3 result)
+// trunc(v) for v in [0, 256): the low mantissa bits of v + 2^23 rounded toward zero
+// (convert_uchar3, :150).  Byte 1 of the result is 0, which pack_rgb0 uses as the padding byte.
+__device__ __forceinline__ uint32_t trunc_bits(float v) {
+  return __float_as_uint(__fadd_rz(v, 8388608.0f));
 }
 
-constexpr int kInterpPx = 4;
+__device__ __forceinline__ uint32_t pack_rgb0(uint32_t c0, uint32_t c1, uint32_t c2) {
+  return __byte_perm(__byte_perm(c0, c1, 0x0040u), c2, 0x5410u);  // c0.b0, c1.b0, c2.b0, 0
+}
 
+constexpr int kInterpPx = 4;      // consecutive pixels per lane: one 16-byte store per row
+constexpr int kInterpRows = 16;   // consecutive rows per warp: the x-axis work is done once
+constexpr int kInterpMaxCols = 136;  // widest reduced-column window a warp stages per row
+
+// Row descriptor, resolved by lane r for row y0 + r and broadcast by shuffle.
+struct RowSel {
+  int rows;   // first reduced row | second reduced row << 16 (equal when ty is 0 or 1)
+  float ty;   // vertical ratio
+  int yex;    // exact-hit reduced row, or -1 when this row is not an exact hit
+};
+
+template <int C>
+__device__ __forceinline__ float vmix_channel(uint32_t a, uint32_t b, float ty) {
+  return mix_rn(byte_to_float<C>(a), byte_to_float<C>(b), ty);
+}
+
+// interpolate_rect, one warp = 128 columns x kInterpRows rows.
+//
+// Everything that depends on x only (table entry, wrap, border fix-ups, clamped reduced columns,
+// ratio) is resolved once per lane; the kInterpRows y entries are resolved by one lane each.
+// The bilinear tap is separable exactly as the reference evaluates it - mix vertically at the two
+// columns, then mix horizontally - so per row a warp first forms the vertical mixes V[c] for the
+// window of reduced columns its 128 pixels touch (one per column, not two per pixel; in the
+// periphery a column serves ~4.6 pixels) in shared memory as floats, then every pixel is one
+// horizontal mix of two staged values.  A ratio of exactly 0 or 1 makes mix() return one operand
+// unchanged, so 1:1 (foveal) columns/rows are handled by selecting that operand: bit-identical,
+// no arithmetic.  Warps that are entirely inside the 1:1 column band skip the staging.
 __global__ void __launch_bounds__(256) sat_interpolate_rect_kernel(const InterpArgs a,
                                                                    const GazeBatch g) {
-  const int x4 = (blockIdx.x * 32 + threadIdx.x) * kInterpPx;
-  const int y = blockIdx.y * 8 + threadIdx.y;
+  __shared__ float4 vstage[8][2][kInterpMaxCols];
+  const int lane = threadIdx.x, warp = threadIdx.y;
+  const int x4 = (blockIdx.x * 32 + lane) * kInterpPx;
+  const int y0 = (blockIdx.y * 8 + warp) * kInterpRows;
   const int f = blockIdx.z;
-  if (x4 >= a.W || y >= a.H) return;
+  if (y0 >= a.H) return;  // warp-uniform
   const int W = a.W, H = a.H, ow = a.ow, oh = a.oh;
   const int cxp = gaze_px(g.xy[2 * f], W);
   const int cyp = gaze_px(g.xy[2 * f + 1], H);
-  const uint32_t *red =
-      reinterpret_cast<const uint32_t *>(a.red + (size_t)f * a.red_stride);
+  const uint32_t *red = reinterpret_cast<const uint32_t *>(a.red + (size_t)f * a.red_stride);
 
-  const int dy = clampi(y - cyp, -H, H);
-  const AxisSel sy = resolve_axis(load_entry(a.ly + (dy + H)), cyp, H, oh, false);
-  const uint32_t *row_lo = red + (size_t)sy.lo * ow;
-  const uint32_t *row_hi = red + (size_t)sy.hi * ow;
-  const uint32_t *row_ex = red + (size_t)sy.exact_idx * ow;
-
-  uint32_t px[kInterpPx];
+  // ---- x axis: once per lane ------------------------------------------------------------
+  int xlo[kInterpPx], xhi[kInterpPx], xex[kInterpPx];
+  float xr[kInterpPx];
+  bool all_deg = true;
+  int cmin = 0x7fffffff, cmax = -1;
 #pragma unroll
   for (int k = 0; k < kInterpPx; ++k) {
-    int x = x4 + k;
-    px[k] = 0;
-    if (x < W) {
-      bool wrapped = false;  // :26-33
-      if (x - cxp > W / 2) {
-        x -= W;
-        wrapped = true;
-      } else if (x - cxp < -(W / 2)) {
-        x += W;
-        wrapped = true;
-      }
-      const int dx = clampi(x - cxp, -W, W);
-      const AxisSel sx = resolve_axis(load_entry(a.lx + (dx + W)), cxp, W, ow, wrapped);
-      if (sx.exact && sy.exact) {  // :67-72
-        px[k] = __ldg(row_ex + sx.exact_idx);
+    int x = min(x4 + k, W - 1);  // lanes past the right edge repeat the last pixel (never stored)
+    bool wrapped = false;        // :26-33
+    if (x - cxp > W / 2) {
+      x -= W;
+      wrapped = true;
+    } else if (x - cxp < -(W / 2)) {
+      x += W;
+      wrapped = true;
+    }
+    const int dx = clampi(x - cxp, -W, W);
+    const AxisSel sx = resolve_axis(load_entry(a.lx + (dx + W)), cxp, W, ow, wrapped);
+    const bool deg = sx.ratio == 0.0f || sx.ratio == 1.0f;
+    const int sel = sx.ratio == 1.0f ? sx.hi : sx.lo;
+    xlo[k] = deg ? sel : sx.lo;  // degenerate: both taps are the selected column
+    xhi[k] = deg ? sel : sx.hi;
+    xr[k] = sx.ratio;
+    xex[k] = sx.exact ? sx.exact_idx : -1;
+    all_deg = all_deg && deg;
+    cmin = min(cmin, min(xlo[k], xhi[k]));
+    cmax = max(cmax, max(xlo[k], xhi[k]));
+  }
+  all_deg = __all_sync(0xffffffffu, all_deg);
+  cmin = __reduce_min_sync(0xffffffffu, cmin);
+  cmax = __reduce_max_sync(0xffffffffu, cmax);
+  const int ncols = cmax - cmin + 1;
+
+  // ---- y axis: lane r resolves row y0 + r --------------------------------------------------
+  RowSel mine;
+  {
+    const int y = min(y0 + (lane & (kInterpRows - 1)), H - 1);
+    const int dy = clampi(y - cyp, -H, H);
+    const AxisSel sy = resolve_axis(load_entry(a.ly + (dy + H)), cyp, H, oh, false);
+    const bool deg = sy.ratio == 0.0f || sy.ratio == 1.0f;
+    const int sel = sy.ratio == 1.0f ? sy.hi : sy.lo;
+    mine.rows = deg ? (sel | (sel << 16)) : (sy.lo | (sy.hi << 16));
+    mine.ty = sy.ratio;
+    mine.yex = sy.exact ? sy.exact_idx : -1;
+  }
+
+  uint32_t *orow = reinterpret_cast<uint32_t *>(a.out + (size_t)f * a.out_stride) +
+                   (size_t)y0 * W + x4;
+  const bool in_x = x4 < W;
+  const bool vec_ok = (x4 + kInterpPx <= W) && ((reinterpret_cast<uintptr_t>(orow) & 15) == 0) &&
+                      ((W & 3) == 0);
+  const int nrows = min(kInterpRows, H - y0);
+
+  auto store_row = [&](const uint32_t (&px)[kInterpPx]) {
+    if (vec_ok) {
+      __stcs(reinterpret_cast<uint4 *>(orow), make_uint4(px[0], px[1], px[2], px[3]));
+    } else if (in_x) {
+#pragma unroll
+      for (int k = 0; k < kInterpPx; ++k)
+        if (x4 + k < W) orow[k] = px[k];
+    }
+  };
+
+  if (all_deg) {
+    // Every pixel of this warp maps onto a single reduced column: vertical mix (or copy) only.
+    for (int r = 0; r < nrows; ++r, orow += W) {
+      const int rows = __shfl_sync(0xffffffffu, mine.rows, r);
+      const float ty = __shfl_sync(0xffffffffu, mine.ty, r);
+      const int yex = __shfl_sync(0xffffffffu, mine.yex, r);
+      const uint32_t *ra = red + (size_t)(rows & 0xffff) * ow;
+      const uint32_t *rb = red + (size_t)(rows >> 16) * ow;
+      uint32_t px[kInterpPx];
+      if ((rows & 0xffff) == (rows >> 16)) {  // warp-uniform: the row is a copy of a reduced row
+        const uint32_t *rex = red + (size_t)max(yex, 0) * ow;
+#pragma unroll
+        for (int k = 0; k < kInterpPx; ++k)
+          px[k] = (yex >= 0 && xex[k] >= 0) ? __ldg(rex + xex[k])  // :67-72: all 4 bytes
+                                            : (__ldg(ra + xlo[k]) & 0x00ffffffu);
       } else {
-        px[k] = lerp_pixel(__ldg(row_lo + sx.lo), __ldg(row_lo + sx.hi), __ldg(row_hi + sx.lo),
-                           __ldg(row_hi + sx.hi), sx.ratio, sy.ratio);
+#pragma unroll
+        for (int k = 0; k < kInterpPx; ++k) {
+          const uint32_t p = __ldg(ra + xlo[k]), q = __ldg(rb + xlo[k]);
+          px[k] = pack_rgb0(trunc_bits(vmix_channel<0>(p, q, ty)),
+                            trunc_bits(vmix_channel<1>(p, q, ty)),
+                            trunc_bits(vmix_channel<2>(p, q, ty)));
+        }
+      }
+      store_row(px);
+    }
+    return;
+  }
+
+  if (ncols <= kInterpMaxCols) {
+    // Stage the vertical mixes of the column window, then one horizontal mix per pixel.
+    int olo[kInterpPx], ohi[kInterpPx];
+#pragma unroll
+    for (int k = 0; k < kInterpPx; ++k) {
+      olo[k] = xlo[k] - cmin;
+      ohi[k] = xhi[k] - cmin;
+    }
+    for (int r = 0; r < nrows; ++r, orow += W) {
+      const int rows = __shfl_sync(0xffffffffu, mine.rows, r);
+      const float ty = __shfl_sync(0xffffffffu, mine.ty, r);
+      const int yex = __shfl_sync(0xffffffffu, mine.yex, r);
+      const uint32_t *ra = red + (size_t)(rows & 0xffff) * ow + cmin;
+      const uint32_t *rb = red + (size_t)(rows >> 16) * ow + cmin;
+      float4 *vs = vstage[warp][r & 1];
+      if ((rows & 0xffff) == (rows >> 16)) {  // warp-uniform
+        for (int c = lane; c < ncols; c += 32) {
+          const uint32_t p = __ldg(ra + c);
+          vs[c] = make_float4(byte_to_float<0>(p), byte_to_float<1>(p), byte_to_float<2>(p), 0.f);
+        }
+      } else {
+        for (int c = lane; c < ncols; c += 32) {
+          const uint32_t p = __ldg(ra + c), q = __ldg(rb + c);
+          vs[c] = make_float4(vmix_channel<0>(p, q, ty), vmix_channel<1>(p, q, ty),
+                              vmix_channel<2>(p, q, ty), 0.f);
+        }
+      }
+      __syncwarp();
+      uint32_t px[kInterpPx];
+#pragma unroll
+      for (int k = 0; k < kInterpPx; ++k) {
+        const float4 l = vs[olo[k]], rr = vs[ohi[k]];
+        px[k] = pack_rgb0(trunc_bits(mix_rn(l.x, rr.x, xr[k])), trunc_bits(mix_rn(l.y, rr.y, xr[k])),
+                          trunc_bits(mix_rn(l.z, rr.z, xr[k])));
+      }
+      if (yex >= 0) {  // warp-uniform: pixels that hit a sample on both axes copy all 4 bytes
+        const uint32_t *rex = red + (size_t)yex * ow;
+#pragma unroll
+        for (int k = 0; k < kInterpPx; ++k)
+          if (xex[k] >= 0) px[k] = __ldg(rex + xex[k]);
+      }
+      store_row(px);
+    }
+    return;
+  }
+
+  // Seam warps (the window spans the whole reduced width): gather every tap directly.
+  for (int r = 0; r < nrows; ++r, orow += W) {
+    const int rows = __shfl_sync(0xffffffffu, mine.rows, r);
+    const float ty = __shfl_sync(0xffffffffu, mine.ty, r);
+    const int yex = __shfl_sync(0xffffffffu, mine.yex, r);
+    const uint32_t *ra = red + (size_t)(rows & 0xffff) * ow;
+    const uint32_t *rb = red + (size_t)(rows >> 16) * ow;
+    const uint32_t *rex = red + (size_t)max(yex, 0) * ow;
+    uint32_t px[kInterpPx];
+#pragma unroll
+    for (int k = 0; k < kInterpPx; ++k) {
+      if (yex >= 0 && xex[k] >= 0) {
+        px[k] = __ldg(rex + xex[k]);
+      } else {
+        const uint32_t tl = __ldg(ra + xlo[k]), tr = __ldg(ra + xhi[k]);
+        const uint32_t bl = __ldg(rb + xlo[k]), br = __ldg(rb + xhi[k]);
+        px[k] = pack_rgb0(
+            trunc_bits(mix_rn(vmix_channel<0>(tl, bl, ty), vmix_channel<0>(tr, br, ty), xr[k])),
+            trunc_bits(mix_rn(vmix_channel<1>(tl, bl, ty), vmix_channel<1>(tr, br, ty), xr[k])),
+            trunc_bits(mix_rn(vmix_channel<2>(tl, bl, ty), vmix_channel<2>(tr, br, ty), xr[k])));
       }
     }
-  }
-  uint32_t *o = reinterpret_cast<uint32_t *>(a.out + (size_t)f * a.out_stride) + (size_t)y * W + x4;
-  if (x4 + kInterpPx <= W && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
-    __stcs(reinterpret_cast<uint4 *>(o), make_uint4(px[0], px[1], px[2], px[3]));
-  } else {
-#pragma unroll
-    for (int k = 0; k < kInterpPx; ++k)
-      if (x4 + k < W) o[k] = px[k];
+    store_row(px);
   }
 }
 
@@ -264,7 +481,9 @@ cudaError_t launch_sat_sample_rect(const LaunchCtx &lc, int n, uint8_t *out, siz
   a.o_linesize_px = out_linesize / 4;  // :153
   a.W = W;
   a.H = H;
-  const dim3 grid((ow + 31) / 32, (oh + 7) / 8, n), block(32, 8);
+  const dim3 grid((ow + kSampleCols - 1) / kSampleCols,
+                  (oh + 8 * kSampleRows - 1) / (8 * kSampleRows), n),
+      block(32, 8);
   KernelScope ks(lc, "sat_sample_rect");
   sat_sample_rect_kernel<<<grid, block, 0, lc.stream>>>(a, gaze);
   return cudaGetLastError();
@@ -285,7 +504,9 @@ cudaError_t launch_sat_interpolate_rect(const LaunchCtx &lc, int n, uint8_t *out
   a.H = H;
   a.ow = ow;
   a.oh = oh;
-  const dim3 grid((W + 32 * kInterpPx - 1) / (32 * kInterpPx), (H + 7) / 8, n), block(32, 8);
+  const dim3 grid((W + 32 * kInterpPx - 1) / (32 * kInterpPx),
+                  (H + 8 * kInterpRows - 1) / (8 * kInterpRows), n),
+      block(32, 8);
   KernelScope ks(lc, "sat_interpolate_rect");
   sat_interpolate_rect_kernel<<<grid, block, 0, lc.stream>>>(a, gaze);
   return cudaGetLastError();
