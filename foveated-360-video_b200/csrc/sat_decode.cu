@@ -6,6 +6,8 @@
 // (sat_decoder_decode_kernel.cl:1-58).  None of the three evaluates a transcendental on the
 // device: the separable, gaze-independent parts of the transform come from host-built 1-D
 // tables (luts.cc), so the kernels are integer/gather work bounded by HBM/L2 bandwidth.
+#include <cstdlib>
+
 #include "fov360_internal.h"
 
 namespace fov {
@@ -53,7 +55,6 @@ struct SampleArgs {
 };
 
 constexpr int kSampleCols = 31;
-constexpr int kSampleRows = 8;
 
 struct Rgb32 {
   uint32_t r, g, b;
@@ -75,6 +76,7 @@ __device__ __forceinline__ Rgb32 shfl_down1(const Rgb32 v) {
   return o;
 }
 
+template <int kSampleRows>
 __global__ void __launch_bounds__(256) sat_sample_rect_kernel(const SampleArgs a,
                                                               const GazeBatch g) {
   const int lane = threadIdx.x;
@@ -109,39 +111,49 @@ __global__ void __launch_bounds__(256) sat_sample_rect_kernel(const SampleArgs a
   const uint32_t *sat =
       reinterpret_cast<const uint32_t *>(reinterpret_cast<const uint8_t *>(a.sat) +
                                          (size_t)f * a.sat_stride);
+  const uint32_t *colL = sat + (size_t)mx * 3;
+  const uint32_t *colR = sat + (size_t)px * 3;
+  const size_t row_words = (size_t)W * 3;
+
+  // Gather the left corner of all kSampleRows+1 horizontal edges up front (27 loads in flight
+  // per lane).  Edge e is the bottom edge of row e-1 and, away from the frame border, the top
+  // edge of row e; it is fetched at the bottom-edge form of its coordinate (:202).
+  int yraw[kSampleRows + 1];
+  Rgb32 L[kSampleRows + 1];
+#pragma unroll
+  for (int e = 0; e <= kSampleRows; ++e) {
+    yraw[e] = cyp + a.yedge[min(j0 + e, oh)];
+    const int ye = (e == 0) ? clampi(yraw[0], 0, H - 2) : clampi(yraw[e], 1, H - 1);
+    L[e] = ld_sat(colL + (size_t)ye * row_words);
+  }
+
+  // The store keeps byte 3 of the target pixel (`.xyz =`, :212): fetch the old pixels now too.
   uint32_t *orow = reinterpret_cast<uint32_t *>(a.out + (size_t)f * a.out_stride) +
                    (size_t)j0 * a.o_linesize_px + i;
+  uint32_t old[kSampleRows];
+#pragma unroll
+  for (int r = 0; r < kSampleRows; ++r)
+    old[r] = (has_px && x_in && j0 + r < oh) ? orow[(size_t)r * a.o_linesize_px] : 0u;
 
-  int prev_y = -1;
-  Rgb32 pl = {0, 0, 0}, pr = {0, 0, 0};  // previous bottom edge: left / right corner
-  const int j1 = min(j0 + kSampleRows, oh);
-  for (int j = j0; j < j1; ++j, orow += a.o_linesize_px) {
-    int py = cyp + a.yedge[j + 1];  // grid[j+1][i+1].y  (:172-173)
-    int my = cyp + a.yedge[j];      // grid[j][i+1].y    (:174-175)
+#pragma unroll
+  for (int r = 0; r < kSampleRows; ++r, orow += a.o_linesize_px) {
+    if (j0 + r >= oh) break;  // warp-uniform
+    int py = yraw[r + 1];     // grid[j+1][i+1].y  (:172-173)
+    int my = yraw[r];         // grid[j][i+1].y    (:174-175)
     const bool y_in = (py >= 0 && py < H) || (my >= 0 && my < H);  // :199-200
-    if (!y_in) {  // warp-uniform: the whole row keeps its contents
-      prev_y = -1;
-      continue;
-    }
-    py = clampi(py, 1, H - 1);  // :202, :204
+    if (!y_in) continue;        // warp-uniform: the whole row keeps its contents
+    py = clampi(py, 1, H - 1);  // :202, :204  (== the coordinate L[r+1] was fetched at)
     my = clampi(my, 0, py - 1);
-    Rgb32 tl, tr;
-    if (my == prev_y) {  // warp-uniform
-      tl = pl;
-      tr = pr;
-    } else {
-      const uint32_t *row = sat + (size_t)my * W * 3;
-      tl = ld_sat(row + (size_t)mx * 3);
-      tr = shfl_down1(tl);
-      if (own_right) tr = ld_sat(row + (size_t)px * 3);
-    }
-    const uint32_t *row = sat + (size_t)py * W * 3;
-    const Rgb32 bl = ld_sat(row + (size_t)mx * 3);
+    const int fetched_top = (r == 0) ? clampi(yraw[0], 0, H - 2) : clampi(yraw[r], 1, H - 1);
+    Rgb32 tl = L[r];
+    if (my != fetched_top) tl = ld_sat(colL + (size_t)my * row_words);  // warp-uniform, borders
+    const Rgb32 bl = L[r + 1];
+    Rgb32 tr = shfl_down1(tl);
     Rgb32 br = shfl_down1(bl);
-    if (own_right) br = ld_sat(row + (size_t)px * 3);
-    pl = bl;
-    pr = br;
-    prev_y = py;
+    if (own_right) {  // seam / border lanes and the last column gather their own right corners
+      tr = ld_sat(colR + (size_t)my * row_words);
+      br = ld_sat(colR + (size_t)py * row_words);
+    }
     if (has_px && x_in) {
       uint32_t s0 = br.r - tr.r + tl.r - bl.r;  // :212-217
       uint32_t s1 = br.g - tr.g + tl.g - bl.g;
@@ -154,7 +166,7 @@ __global__ void __launch_bounds__(256) sat_sample_rect_kernel(const SampleArgs a
         s2 = udiv_exact(s2, area, rcp);
       }
       // `.xyz =` store: byte 3 of the uchar4 keeps its previous value (:212).
-      *orow = (*orow & 0xff000000u) | (s0 & 0xffu) | ((s1 & 0xffu) << 8) | ((s2 & 0xffu) << 16);
+      *orow = (old[r] & 0xff000000u) | (s0 & 0xffu) | ((s1 & 0xffu) << 8) | ((s2 & 0xffu) << 16);
     }
   }
 }
@@ -481,11 +493,18 @@ cudaError_t launch_sat_sample_rect(const LaunchCtx &lc, int n, uint8_t *out, siz
   a.o_linesize_px = out_linesize / 4;  // :153
   a.W = W;
   a.H = H;
-  const dim3 grid((ow + kSampleCols - 1) / kSampleCols,
-                  (oh + 8 * kSampleRows - 1) / (8 * kSampleRows), n),
+  static const int rows_per_warp = [] {
+    const char *e = getenv("FOV360_SAMPLE_ROWS");
+    return e ? atoi(e) : 4;
+  }();
+  const int rpw = rows_per_warp == 8 ? 8 : 4;
+  const dim3 grid((ow + kSampleCols - 1) / kSampleCols, (oh + 8 * rpw - 1) / (8 * rpw), n),
       block(32, 8);
   KernelScope ks(lc, "sat_sample_rect");
-  sat_sample_rect_kernel<<<grid, block, 0, lc.stream>>>(a, gaze);
+  if (rpw == 8)
+    sat_sample_rect_kernel<8><<<grid, block, 0, lc.stream>>>(a, gaze);
+  else
+    sat_sample_rect_kernel<4><<<grid, block, 0, lc.stream>>>(a, gaze);
   return cudaGetLastError();
 }
 
