@@ -17,8 +17,10 @@ struct fov_ctx {
   std::string last_error;
   uint64_t launches = 0;
   Profiler prof;
-  LaunchCtx lc() { return LaunchCtx{stream, sm_count, &prof, &launches}; }
+  LaunchCtx lc() { return LaunchCtx{stream, sm_count, device, &prof, &launches}; }
   SatScratch sat_scratch;
+  std::tuple<int, int, int, int, int> sat_layout{0, 0, 0, 0, 0};  // (n, W, H, R, NW) of the flags
+  uint32_t sat_epoch = 0;
   std::map<std::tuple<int, int, int, int>, SatGrid> sat_grids;
   std::map<std::tuple<int, int, int, int>, InterpLut> interp_luts;
   std::map<std::tuple<int, int, int, int>, ImgGrid> img_grids;
@@ -175,7 +177,9 @@ int get_lp_grid(fov_ctx *ctx, int ow, int oh, const LogpolarGrid **out) {
 }
 
 int ensure_sat_scratch(fov_ctx *ctx, int n, int W, int H) {
-  const size_t need = sat_scratch_bytes(n, W, H);
+  size_t need = sat_scratch_bytes(n, W, H);
+  const size_t need1 = sat_onepass_plan(n, W, H).bytes;
+  if (need1 > need) need = need1;
   if (need <= ctx->sat_scratch.bytes) return FOV_OK;
   if (ctx->sat_scratch.base) {
     FOV_CUDA(ctx, cudaStreamSynchronize(ctx->stream), "sat scratch resize");
@@ -184,6 +188,7 @@ int ensure_sat_scratch(fov_ctx *ctx, int n, int W, int H) {
   }
   FOV_CUDA(ctx, cudaMalloc(&ctx->sat_scratch.base, need), "sat scratch alloc");
   ctx->sat_scratch.bytes = need;
+  ctx->sat_layout = std::make_tuple(0, 0, 0, 0, 0);  // forces the flag arrays to be cleared
   return FOV_OK;
 }
 
@@ -392,6 +397,24 @@ int fov_sat_encode_batched(fov_ctx *ctx, int n, uint32_t *sat, size_t sat_stride
   DeviceGuard g(ctx);
   int rc = ensure_sat_scratch(ctx, n, W, H);
   if (rc) return rc;
+  if (sat_onepass_eligible(sat, sat_stride, src, src_stride, W, H, linesize)) {
+    const SatOnePassPlan p = sat_onepass_plan(n, W, H);
+    const auto key = std::make_tuple(n, W, H, p.R, p.NW);
+    if (key != ctx->sat_layout || ctx->sat_epoch >= 0x3ffffff0u) {
+      // new tile geometry (or epoch wrap): the ticket counters and carry flags start from zero
+      FOV_CUDA(ctx, cudaMemsetAsync(ctx->sat_scratch.base, 0, p.clear_bytes, ctx->stream),
+               "sat scratch clear");
+      ctx->sat_layout = key;
+      ctx->sat_epoch = 0;
+    }
+    FOV_CUDA(ctx,
+             launch_sat_onepass(ctx->lc(), n, sat, sat_stride, src, src_stride, W, H, linesize,
+                                ctx->sat_scratch.base, ++ctx->sat_epoch),
+             "sat encode launch");
+    return FOV_OK;
+  }
+  // Unaligned or 3-byte-pixel sources: the three-kernel reduce / carry / scan path.
+  ctx->sat_layout = std::make_tuple(0, 0, 0, 0, 0);  // it reuses the same scratch bytes
   FOV_CUDA(ctx,
            launch_sat_encode(ctx->lc(), n, sat, sat_stride, src, src_stride, W, H, linesize,
                              ctx->sat_scratch.base),

@@ -92,6 +92,7 @@ struct Profiler {
 struct LaunchCtx {
   cudaStream_t stream = nullptr;
   int sm_count = 148;
+  int device = 0;
   Profiler *prof = nullptr;
   uint64_t *launches = nullptr;
 };
@@ -137,6 +138,18 @@ size_t sat_scratch_bytes(int n, int W, int H);
 cudaError_t launch_sat_encode(const LaunchCtx &lc, int n, uint32_t *sat, size_t sat_stride,
                               const uint8_t *src, size_t src_stride, int W, int H, int linesize,
                               void *scratch);
+
+// Single-pass SAT build (sat_onepass.cu): tile geometry and scratch layout for (n, W, H).
+struct SatOnePassPlan {
+  int NW, R, nb, ns, nsc;
+  size_t off_counters, off_flag_left, off_flag_col, off_rowagg, off_colagg, bytes, clear_bytes;
+};
+SatOnePassPlan sat_onepass_plan(int n, int W, int H);
+bool sat_onepass_eligible(const uint32_t *sat, size_t sat_stride, const uint8_t *src,
+                          size_t src_stride, int W, int H, int linesize);
+cudaError_t launch_sat_onepass(const LaunchCtx &lc, int n, uint32_t *sat, size_t sat_stride,
+                               const uint8_t *src, size_t src_stride, int W, int H, int linesize,
+                               void *scratch, uint32_t epoch);
 
 cudaError_t launch_sat_sample_rect(const LaunchCtx &lc, int n, uint8_t *out, size_t out_stride, int ow,
                                    int oh, int out_linesize, const uint32_t *sat,
