@@ -270,12 +270,10 @@ def run_gpu_arm(args, W, H, ow, oh, rank, world, local_rank):
     barrier()
     clocks = sampler.result()
     launches = m.launch_count - launches0
-    ms = e0.elapsed_time(e1)
-    if dist:
-        t = torch.tensor([ms], device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
-    fps = world * B * K / (ms * 1e-3)
+    # whole-job rate = all frames of all ranks / the slowest rank's device time
+    ms = fov.sharding.reduce_max_seconds(e0.elapsed_time(e1), dist, "cuda")
+    frames_total = fov.sharding.reduce_sum_int(B * K, dist, "cuda")
+    fps = frames_total / (ms * 1e-3)
 
     # ---- per-kernel pass (same K steps, every launch bracketed by CUDA events on the stream) ----
     m.profile_reset()
@@ -386,13 +384,7 @@ def run_e2e(args, fov, device, W, H, ow, oh, frames, gaze, dist, world):
     for i in range(K):
         step(Wm + i)
     sync()
-    dt = time.perf_counter() - t0
-    if dist:
-        import torch
-
-        t = torch.tensor([dt], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dt = float(t.item())
+    dt = fov.sharding.reduce_max_seconds(time.perf_counter() - t0, dist, "cuda")
     checksum = int(hout[: 4 * W].astype(np.uint32).sum())  # the result really is on the host
     for ln in lanes:
         for k in ("src", "sat", "red", "full"):

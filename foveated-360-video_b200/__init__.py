@@ -6,6 +6,7 @@ builds and binds it for the tests and the benchmark; the directory name contains
 it with ``importlib.import_module("foveated-360-video_b200")`` (see ``__graft_entry__.py``).
 """
 from . import build as build_module  # noqa: F401
+from . import sharding  # noqa: F401
 from ._capi import PROTOTYPES, header_symbols, library_path, load  # noqa: F401
 from .host import (  # noqa: F401
     DeviceBuffer,
