@@ -296,9 +296,16 @@ def run_gpu_arm(args, W, H, ow, oh, rank, world, local_rank):
         kernels[name] = {"ms_per_launch": round(per_launch_ms, 4), "launches": cnt,
                          "share": round(tot / K / step_ms, 4), "alg_gbs": round(gbs, 1)}
     dom = max(totals, key=lambda k: totals[k][0])
+    traffic = None
+    try:  # measured DRAM bytes per launch of the dominant kernel, from the committed ncu capture
+        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as fh:
+            t = json.load(fh)[args.workload][str(B)][dom]
+            traffic = t["dram_read"] + t["dram_write"]
+    except Exception:
+        pass
     roofline = {
         "bound": "hbm", "kernel": dom, "achieved": kernels[dom]["alg_gbs"], "peak": peak,
-        "unit": "GB/s", "frac": round(kernels[dom]["alg_gbs"] / peak, 4), "traffic": None,
+        "unit": "GB/s", "frac": round(kernels[dom]["alg_gbs"] / peak, 4), "traffic": traffic,
         "peak_source": peak_src,
         "algorithmic_bytes_per_launch": kernel_bytes.get(dom, 0) * B,
         "pipeline": {"bytes_per_frame": ab["total"],
