@@ -139,10 +139,18 @@ def load_cpu_oracle():
 
     try:
         if os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libfovref.so")) or O.ref_available():
-            return O.Oracle("ref"), "reference"
+            orc, kind = O.Oracle("ref"), "reference"
+        else:
+            orc, kind = O.Oracle("port"), "port"
     except Exception:
-        pass
-    return O.Oracle("port"), "port"
+        orc, kind = O.Oracle("port"), "port"
+    # all host cores the process may use (torchrun exports OMP_NUM_THREADS=1 for its workers)
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except AttributeError:
+        cores = os.cpu_count() or 1
+    orc.set_threads(cores)
+    return orc, kind
 
 
 def cpu_pipeline_once(orc, frame, ow, oh, cx, cy, grid):

@@ -10,6 +10,7 @@ every operation separately (see the header of that file).
 from __future__ import annotations
 
 import concurrent.futures as cf
+import fcntl
 import hashlib
 import os
 import shutil
@@ -48,7 +49,8 @@ MANIFEST = os.path.join(HERE, "libfov360.manifest")
 
 def _digest(paths: list[str]) -> str:
     """Content hash of the build inputs: mtimes do not survive the snapshot to the GPU box."""
-    h = hashlib.sha256(" ".join(NVCC_FLAGS).encode())
+    # flags without the checkout-dependent absolute include paths
+    h = hashlib.sha256(" ".join(f for f in NVCC_FLAGS if not f.startswith(ROOT)).encode())
     for p in paths:
         with open(p, "rb") as fh:
             h.update(p.rsplit(os.sep, 1)[-1].encode() + b"\0" + fh.read())
@@ -83,6 +85,17 @@ def build(force: bool = False, verbose: bool = False) -> str:
                 return LIB_PATH
     nvcc = nvcc_path()
     os.makedirs(OBJ_DIR, exist_ok=True)
+    # one builder at a time (torchrun starts one process per GPU against the same tree)
+    with open(os.path.join(OBJ_DIR, ".lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        if not force and os.path.exists(LIB_PATH) and os.path.exists(MANIFEST):
+            with open(MANIFEST) as fh:
+                if fh.read().strip() == digest:
+                    return LIB_PATH  # another process finished the build while we waited
+        return _build_locked(nvcc, srcs, digest, force, verbose)
+
+
+def _build_locked(nvcc: str, srcs: list[str], digest: str, force: bool, verbose: bool) -> str:
     objs = [os.path.join(OBJ_DIR, os.path.splitext(s)[0] + ".o") for s in SOURCES]
     todo = [(s, o) for s, o in zip(srcs, objs)
             if force or _stale(o, [s] + HEADERS + [os.path.abspath(__file__)])]
@@ -90,7 +103,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     with cf.ThreadPoolExecutor(max_workers=max(1, min(len(todo), os.cpu_count() or 1))) as ex:
         for fut in [ex.submit(_compile, nvcc, s, o, verbose) for s, o in todo]:
             fut.result()
-    tmp = LIB_PATH + ".tmp"
+    tmp = LIB_PATH + ".tmp%d" % os.getpid()
     subprocess.check_call([nvcc, *ARCH, "-shared", "-cudart", "static", "-o", tmp, *objs])
     os.replace(tmp, LIB_PATH)
     with open(MANIFEST + ".tmp", "w") as fh:
