@@ -246,7 +246,7 @@ __device__ __forceinline__ uint32_t pack_rgb0(uint32_t c0, uint32_t c1, uint32_t
 }
 
 constexpr int kInterpPx = 4;      // consecutive pixels per lane: one 16-byte store per row
-constexpr int kInterpRows = 16;   // consecutive rows per warp: the x-axis work is done once
+constexpr int kInterpRows = 32;   // consecutive rows per warp: the x-axis work is done once
 constexpr int kInterpMaxCols = 136;  // widest reduced-column window a warp stages per row
 
 // Row descriptor, resolved by lane r for row y0 + r and broadcast by shuffle.
@@ -272,8 +272,8 @@ __device__ __forceinline__ float vmix_channel(uint32_t a, uint32_t b, float ty) 
 // horizontal mix of two staged values.  A ratio of exactly 0 or 1 makes mix() return one operand
 // unchanged, so 1:1 (foveal) columns/rows are handled by selecting that operand: bit-identical,
 // no arithmetic.  Warps that are entirely inside the 1:1 column band skip the staging.
-__global__ void __launch_bounds__(256) sat_interpolate_rect_kernel(const InterpArgs a,
-                                                                   const GazeBatch g) {
+__global__ void __launch_bounds__(256, 4) sat_interpolate_rect_kernel(const InterpArgs a,
+                                                                      const GazeBatch g) {
   __shared__ float4 vstage[8][2][kInterpMaxCols];
   const int lane = threadIdx.x, warp = threadIdx.y;
   const int x4 = (blockIdx.x * 32 + lane) * kInterpPx;

@@ -47,7 +47,6 @@ namespace {
 
 constexpr int kMaxWarps = 8;
 constexpr int kMaxBandRows = 64;
-constexpr int kLoadDepth = 16;  // rows in flight per lane while reducing
 constexpr uint32_t kAgg = 1, kInc = 2;  // column-carry states (low 2 bits of a flag word)
 
 struct OnePassArgs {
@@ -57,6 +56,7 @@ struct OnePassArgs {
   int W, H, linesize;
   int n, R, nb, ns, nsc;  // frames, band rows, bands, warp strips, CTA strips
   uint32_t epoch, total_tiles;
+  int debug_nowait;  // timing experiments only: skip the carry waits (WRONG results)
   uint32_t *counters;  // [0] ticket, [1] finished CTAs
   uint32_t *flag_left;  // [tile]               == epoch when rowagg[tile] is published
   uint4 *rowagg;        // [tile][kMaxBandRows] per-row sums of a CTA tile
@@ -96,8 +96,10 @@ __device__ __forceinline__ void add12(uint32_t (&d)[12], const uint4 a, const ui
   d[8] += c.x, d[9] += c.y, d[10] += c.z, d[11] += c.w;
 }
 
-template <bool TMA_STORE>
-__global__ void __launch_bounds__(kMaxWarps * 32, FOV360_ONEPASS_MIN_CTAS) sat_onepass_kernel(const OnePassArgs a) {
+// STORE: 1 = cp.async.bulk (TMA) store of the staged row, 2 = staged row re-read lane-contiguously
+// and written with three fully coalesced 16-byte stores per lane.
+template <int STORE, int MIN_CTAS, int kLoadDepth, int U>
+__global__ void __launch_bounds__(kMaxWarps * 32, MIN_CTAS) sat_onepass_kernel(const OnePassArgs a) {
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ uint32_t s_ticket;
   __shared__ uint4 s_lsum;
@@ -105,7 +107,8 @@ __global__ void __launch_bounds__(kMaxWarps * 32, FOV360_ONEPASS_MIN_CTAS) sat_o
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   uint8_t *stage = smem;  // [NW][kStageBufs][kRowBytes]
-  uint4 *s_rs = reinterpret_cast<uint4 *>(smem + (TMA_STORE ? (size_t)NW * kStageBufs * kRowBytes : 0));
+  constexpr bool TMA_STORE = STORE == 1;
+  uint4 *s_rs = reinterpret_cast<uint4 *>(smem + (size_t)NW * kStageBufs * kRowBytes);
   uint4 *s_left = s_rs + NW * kMaxBandRows;  // [kMaxBandRows] carry from the CTAs to the left
   uint4 *s_wt = s_left + kMaxBandRows;       // [kMaxWarps]    per-warp tile totals
 
@@ -195,7 +198,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32, FOV360_ONEPASS_MIN_CTAS) sat_o
   for (int q = warp; q < s; q += NW) {
     const uint32_t pt = tile - (uint32_t)s + (uint32_t)q;
     if (lane == 0)
-      while (ld_acquire(&a.flag_left[pt]) != a.epoch) __nanosleep(40);
+      while (ld_acquire(&a.flag_left[pt]) != a.epoch && !a.debug_nowait) __nanosleep(40);
     __syncwarp();
     for (int r = lane; r < rows; r += 32) {
       const uint4 v = __ldcg(&a.rowagg[(size_t)pt * kMaxBandRows + r]);
@@ -268,7 +271,9 @@ __global__ void __launch_bounds__(kMaxWarps * 32, FOV360_ONEPASS_MIN_CTAS) sat_o
       while (true) {
         uint32_t st = 0;
         if (lane == 0)
-          while (((st = ld_acquire(&a.flag_col[pc])) >> 2) != a.epoch) __nanosleep(20);
+          while (((st = ld_acquire(&a.flag_col[pc])) >> 2) != a.epoch && !a.debug_nowait)
+            __nanosleep(20);
+        if (a.debug_nowait) st = kInc;
         st = __shfl_sync(0xffffffffu, st, 0);
         if ((st & 3u) == kInc) {  // T_{k+1} = last SAT row of band k: final
           if (in_x) {
@@ -303,10 +308,9 @@ __global__ void __launch_bounds__(kMaxWarps * 32, FOV360_ONEPASS_MIN_CTAS) sat_o
     // ---- phase C: re-read the strip (L2), scan each row, accumulate down, write once ----------
     const uint4 *rc = s_rs + warp * kMaxBandRows;  // exclusive prefix over the CTA's warps
     const int strip_px = min(kStripPx, a.W - strip * kStripPx);
-    uint8_t *my_stage = stage + (TMA_STORE ? (size_t)warp * kStageBufs * kRowBytes : 0);
+    uint8_t *my_stage = stage + (size_t)warp * kStageBufs * kRowBytes;
     const uint64_t policy = pol_stream;
     int buf = 0;
-    constexpr int U = 4;
     uint4 p[U];
 #pragma unroll
     for (int u = 0; u < U; ++u)
@@ -364,11 +368,22 @@ __global__ void __launch_bounds__(kMaxWarps * 32, FOV360_ONEPASS_MIN_CTAS) sat_o
                   : "memory");
             }
             buf = (buf + 1 == kStageBufs) ? 0 : buf + 1;
-          } else if (in_x) {
-            uint4 *d = reinterpret_cast<uint4 *>(drow + (size_t)x0 * 3);
-            __stcs(d + 0, make_uint4(acc[0], acc[1], acc[2], acc[3]));
-            __stcs(d + 1, make_uint4(acc[4], acc[5], acc[6], acc[7]));
-            __stcs(d + 2, make_uint4(acc[8], acc[9], acc[10], acc[11]));
+          } else {
+            // transpose through shared memory so that each store instruction of the warp covers
+            // 512 contiguous bytes (lane-strided 48-byte stores run at ~60 % of this)
+            uint8_t *sb = my_stage + (size_t)buf * kRowBytes;
+            uint4 *sd = reinterpret_cast<uint4 *>(sb + lane * 48);
+            sd[0] = make_uint4(acc[0], acc[1], acc[2], acc[3]);
+            sd[1] = make_uint4(acc[4], acc[5], acc[6], acc[7]);
+            sd[2] = make_uint4(acc[8], acc[9], acc[10], acc[11]);
+            __syncwarp();
+            const uint4 *sl = reinterpret_cast<const uint4 *>(sb) + lane;
+            uint4 *d = reinterpret_cast<uint4 *>(drow + (size_t)strip * kStripPx * 3) + lane;
+            const int n16 = strip_px * 3 / 4;  // 16-byte words in this row segment
+#pragma unroll
+            for (int k = 0; k < 3; ++k)
+              if (k * 32 + lane < n16) __stcs(d + k * 32, sl[k * 32]);
+            buf ^= 1;
           }
         }
       }
@@ -457,6 +472,8 @@ cudaError_t launch_sat_onepass(const LaunchCtx &lc, int n, uint32_t *sat, size_t
   a.ns = p.ns;
   a.nsc = p.nsc;
   a.epoch = epoch;
+  static const int nowait = env_int("FOV360_SAT_DEBUG_NOWAIT", 0);
+  a.debug_nowait = nowait;
   a.total_tiles = (uint32_t)((size_t)n * p.nb * p.nsc);
   a.counters = reinterpret_cast<uint32_t *>(base + p.off_counters);
   a.flag_left = reinterpret_cast<uint32_t *>(base + p.off_flag_left);
@@ -464,24 +481,28 @@ cudaError_t launch_sat_onepass(const LaunchCtx &lc, int n, uint32_t *sat, size_t
   a.flag_col = reinterpret_cast<uint32_t *>(base + p.off_flag_col);
   a.colagg = reinterpret_cast<uint32_t *>(base + p.off_colagg);
 
-  static const bool tma_store = env_int("FOV360_SAT_TMA_STORE", 1) != 0;
+  static const bool tma_store = env_int("FOV360_SAT_TMA_STORE", 0) != 0;
   const size_t carry_smem = (size_t)(p.NW * kMaxBandRows + kMaxBandRows + kMaxWarps) * 16;
-  const size_t smem = carry_smem + (tma_store ? (size_t)p.NW * kStageBufs * kRowBytes : 0);
-  static bool attr_set[64] = {};
-  if (!attr_set[lc.device & 63]) {
-    const int max_smem = (kMaxWarps * kMaxBandRows + kMaxBandRows + kMaxWarps) * 16 +
-                         kMaxWarps * kStageBufs * kRowBytes;
-    cudaFuncSetAttribute(sat_onepass_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         max_smem);
-    cudaFuncSetAttribute(sat_onepass_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         max_smem);
-    attr_set[lc.device & 63] = true;
-  }
+  const size_t smem = carry_smem + (size_t)p.NW * kStageBufs * kRowBytes;
+  const int max_smem = (kMaxWarps * kMaxBandRows + kMaxBandRows + kMaxWarps) * 16 +
+                       kMaxWarps * kStageBufs * kRowBytes;
   KernelScope ks(lc, "sat_onepass");
+  static const int variant = env_int("FOV360_SAT_VARIANT", 0);
+#define FOV_LAUNCH(TMA, MINC, DEPTH, UU)                                                          \
+  do {                                                                                             \
+    cudaFuncSetAttribute(sat_onepass_kernel<TMA, MINC, DEPTH, UU>,                                 \
+                         cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);                   \
+    sat_onepass_kernel<TMA, MINC, DEPTH, UU><<<a.total_tiles, p.NW * 32, smem, lc.stream>>>(a);    \
+  } while (0)
   if (tma_store)
-    sat_onepass_kernel<true><<<a.total_tiles, p.NW * 32, smem, lc.stream>>>(a);
+    FOV_LAUNCH(1, 3, 8, 4);
+  else if (variant == 1)
+    FOV_LAUNCH(2, 4, 8, 2);
+  else if (variant == 2)
+    FOV_LAUNCH(2, 3, 16, 4);
   else
-    sat_onepass_kernel<false><<<a.total_tiles, p.NW * 32, smem, lc.stream>>>(a);
+    FOV_LAUNCH(2, 3, 8, 4);
+#undef FOV_LAUNCH
   return cudaGetLastError();
 }
 
