@@ -142,7 +142,7 @@ cudaError_t launch_sat_encode(const LaunchCtx &lc, int n, uint32_t *sat, size_t 
 // Single-pass SAT build (sat_onepass.cu): tile geometry and scratch layout for (n, W, H).
 struct SatOnePassPlan {
   int NW, R, nb, ns, nsc;
-  size_t off_counters, off_flag_left, off_flag_col, off_rowagg, off_colagg, bytes, clear_bytes;
+  size_t off_counters, off_rowagg, off_colagg, bytes, clear_bytes;
 };
 SatOnePassPlan sat_onepass_plan(int n, int W, int H);
 bool sat_onepass_eligible(const uint32_t *sat, size_t sat_stride, const uint8_t *src,

@@ -68,4 +68,17 @@ __device__ __forceinline__ void warp_scan3(uint32_t &a, uint32_t &b, uint32_t &c
   }
 }
 
+// Inclusive warp scan of two independent u32 values.
+__device__ __forceinline__ void warp_scan2(uint32_t &a, uint32_t &b, int lane) {
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const uint32_t ta = __shfl_up_sync(0xffffffffu, a, d);
+    const uint32_t tb = __shfl_up_sync(0xffffffffu, b, d);
+    if (lane >= d) {
+      a += ta;
+      b += tb;
+    }
+  }
+}
+
 }  // namespace fov

@@ -56,22 +56,42 @@ struct OnePassArgs {
   int W, H, linesize;
   int n, R, nb, ns, nsc;  // frames, band rows, bands, warp strips, CTA strips
   uint32_t epoch, total_tiles;
-  int debug_nowait;  // timing experiments only: skip the carry waits (WRONG results)
+  int policy;  // L2 eviction-hint experiment selector (FOV360_SAT_POLICY)
   uint32_t *counters;  // [0] ticket, [1] finished CTAs
-  uint32_t *flag_left;  // [tile]               == epoch when rowagg[tile] is published
-  uint4 *rowagg;        // [tile][kMaxBandRows] per-row sums of a CTA tile
-  uint32_t *flag_col;   // [tile][NW]           epoch << 2 | state
-  uint32_t *colagg;     // [tile][NW][384]      band aggregate G of a warp strip
+  uint4 *rowagg;       // [tile][kMaxBandRows]  {r, g, b, epoch}: per-row sums of a CTA tile
+  uint4 *colagg;       // [tile][NW][4][32]     {v0, v1, v2, epoch << 2 | state}: column carry
+#ifdef FOV360_SAT_TRACE
+  long long *trace;  // [tile][8] clock64 at the phase boundaries (tools/sat_trace.cu only)
+#endif
 };
 
-__device__ __forceinline__ uint32_t ld_acquire(const uint32_t *p) {
-  uint32_t v;
-  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
+#ifdef FOV360_SAT_TRACE
+#define FOV_TRACE(i) \
+  if (threadIdx.x == 0) a.trace[(size_t)tile * 8 + (i)] = clock64()
+#else
+#define FOV_TRACE(i)
+#endif
+
+// Carries travel between CTAs as self-validating 16-byte units {three words, tag}: one
+// single-copy-atomic 128-bit store publishes data and tag together, the consumer polls the unit
+// itself.  No release fence (MEMBAR.GPU has to drain every store the SM has in flight - several
+// microseconds while the neighbours stream SAT rows), no separate flag round trip.
+__device__ __forceinline__ uint4 ld_unit(const uint4 *p) {
+  uint64_t lo, hi;
+  asm volatile(
+      "{\n\t.reg .b128 q;\n\tld.relaxed.gpu.global.b128 q, [%2];\n\tmov.b128 {%0, %1}, q;\n\t}"
+      : "=l"(lo), "=l"(hi)
+      : "l"(p)
+      : "memory");
+  return make_uint4((uint32_t)lo, (uint32_t)(lo >> 32), (uint32_t)hi, (uint32_t)(hi >> 32));
 }
 
-__device__ __forceinline__ void st_release(uint32_t *p, uint32_t v) {
-  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+__device__ __forceinline__ void st_unit(uint4 *p, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
+  const uint64_t lo = (uint64_t)x | ((uint64_t)y << 32), hi = (uint64_t)z | ((uint64_t)w << 32);
+  asm volatile(
+      "{\n\t.reg .b128 q;\n\tmov.b128 q, {%1, %2};\n\tst.relaxed.gpu.global.b128 [%0], q;\n\t}" ::"l"(p),
+      "l"(lo), "l"(hi)
+      : "memory");
 }
 
 // 128-bit streaming load with an explicit L2 eviction policy (createpolicy handle).
@@ -89,32 +109,26 @@ __device__ __forceinline__ uint4 load_row4(const uint8_t *row, int x0, int W, ui
   return v;
 }
 
-__device__ __forceinline__ void add12(uint32_t (&d)[12], const uint4 a, const uint4 b,
-                                      const uint4 c) {
-  d[0] += a.x, d[1] += a.y, d[2] += a.z, d[3] += a.w;
-  d[4] += b.x, d[5] += b.y, d[6] += b.z, d[7] += b.w;
-  d[8] += c.x, d[9] += c.y, d[10] += c.z, d[11] += c.w;
-}
-
 // STORE: 1 = cp.async.bulk (TMA) store of the staged row, 2 = staged row re-read lane-contiguously
 // and written with three fully coalesced 16-byte stores per lane.
 template <int STORE, int MIN_CTAS, int kLoadDepth, int U>
 __global__ void __launch_bounds__(kMaxWarps * 32, MIN_CTAS) sat_onepass_kernel(const OnePassArgs a) {
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ uint32_t s_ticket;
-  __shared__ uint4 s_lsum;
+  constexpr bool TMA_STORE = STORE == 1;
+  constexpr int kBufs = TMA_STORE ? kStageBufs : 2;
   const int NW = blockDim.x >> 5;
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
-  uint8_t *stage = smem;  // [NW][kStageBufs][kRowBytes]
-  constexpr bool TMA_STORE = STORE == 1;
-  uint4 *s_rs = reinterpret_cast<uint4 *>(smem + (size_t)NW * kStageBufs * kRowBytes);
+  uint8_t *stage = smem;  // [NW][kBufs][kRowBytes]
+  uint4 *s_rs = reinterpret_cast<uint4 *>(smem + (size_t)NW * kBufs * kRowBytes);
   uint4 *s_left = s_rs + NW * kMaxBandRows;  // [kMaxBandRows] carry from the CTAs to the left
-  uint4 *s_wt = s_left + kMaxBandRows;       // [kMaxWarps]    per-warp tile totals
 
   if (threadIdx.x == 0) s_ticket = atomicAdd(&a.counters[0], 1u);
+  if (threadIdx.x < kMaxBandRows) s_left[threadIdx.x] = make_uint4(0, 0, 0, 0);
   __syncthreads();
   const uint32_t tile = s_ticket;  // (band, frame, strip) order
+  FOV_TRACE(0);
   const int s = (int)(tile % (uint32_t)a.nsc);
   const int f = (int)((tile / (uint32_t)a.nsc) % (uint32_t)a.n);
   const int b = (int)(tile / ((uint32_t)a.nsc * (uint32_t)a.n));
@@ -134,13 +148,20 @@ __global__ void __launch_bounds__(kMaxWarps * 32, MIN_CTAS) sat_onepass_kernel(c
   uint64_t pol_keep, pol_stream;
   asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol_keep));
   asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_stream));
+  if (a.policy) {
+    uint64_t pol_normal;
+    asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pol_normal));
+    if (a.policy == 1) pol_keep = pol_normal;
+    if (a.policy == 2) pol_keep = pol_normal, pol_stream = pol_normal;
+    if (a.policy == 3) pol_stream = pol_normal;
+  }
 
   // ---- phase A: read the strip once; column sums per lane, row sums per row ------------------
-  uint32_t acc[12];
-#pragma unroll
-  for (int i = 0; i < 12; ++i) acc[i] = 0;
+  // Sums of at most 64 rows (columns) or 128 pixels (rows) of bytes fit 16 bits, so two channels
+  // share a register: (R | B << 16) and G.
+  uint32_t crb[4] = {0, 0, 0, 0}, cg[4] = {0, 0, 0, 0};
   for (int yc = y0; yc < y1; yc += 32) {
-    uint32_t k0 = 0, k1 = 0, k2 = 0;
+    uint32_t krb = 0, kg = 0;
     const int nr = min(32, y1 - yc);
     for (int r8 = 0; r8 < nr; r8 += kLoadDepth) {
       uint4 q[kLoadDepth];
@@ -152,30 +173,26 @@ __global__ void __launch_bounds__(kMaxWarps * 32, MIN_CTAS) sat_onepass_kernel(c
 #pragma unroll
       for (int u = 0; u < kLoadDepth; ++u) {
         if (r8 + u < nr) {
-          uint32_t p[12];
-          unpack_px4(q[u], p);
+          const uint32_t w[4] = {q[u].x, q[u].y, q[u].z, q[u].w};
+          uint32_t trb = 0, tg = 0;
 #pragma unroll
-          for (int i = 0; i < 12; ++i) acc[i] += p[i];
-          const uint32_t t0 = __reduce_add_sync(0xffffffffu, p[0] + p[3] + p[6] + p[9]);
-          const uint32_t t1 = __reduce_add_sync(0xffffffffu, p[1] + p[4] + p[7] + p[10]);
-          const uint32_t t2 = __reduce_add_sync(0xffffffffu, p[2] + p[5] + p[8] + p[11]);
-          if (lane == r8 + u) {
-            k0 = t0;
-            k1 = t1;
-            k2 = t2;
+          for (int k = 0; k < 4; ++k) {
+            const uint32_t rb = w[k] & 0x00ff00ffu, g = __byte_perm(w[k], 0, 0x4441);
+            crb[k] += rb, cg[k] += g;
+            trb += rb, tg += g;
           }
+          trb = __reduce_add_sync(0xffffffffu, trb);
+          tg = __reduce_add_sync(0xffffffffu, tg);
+          if (lane == r8 + u) krb = trb, kg = tg;
         }
       }
     }
-    if (lane < nr) s_rs[warp * kMaxBandRows + (yc - y0) + lane] = make_uint4(k0, k1, k2, 0);
+    if (lane < nr)
+      s_rs[warp * kMaxBandRows + (yc - y0) + lane] = make_uint4(krb & 0xffffu, kg, krb >> 16, 0);
   }
-  {
-    const uint32_t t0 = __reduce_add_sync(0xffffffffu, acc[0] + acc[3] + acc[6] + acc[9]);
-    const uint32_t t1 = __reduce_add_sync(0xffffffffu, acc[1] + acc[4] + acc[7] + acc[10]);
-    const uint32_t t2 = __reduce_add_sync(0xffffffffu, acc[2] + acc[5] + acc[8] + acc[11]);
-    if (lane == 0) s_wt[warp] = make_uint4(t0, t1, t2, 0);
-  }
+  FOV_TRACE(1);
   __syncthreads();
+  FOV_TRACE(2);
 
   // ---- row sums: exclusive prefix over the CTA's warps, publish the CTA totals ---------------
   if ((int)threadIdx.x < rows) {
@@ -186,53 +203,64 @@ __global__ void __launch_bounds__(kMaxWarps * 32, MIN_CTAS) sat_onepass_kernel(c
       s_rs[w * kMaxBandRows + r] = make_uint4(r0, r1, r2, 0);
       r0 += v.x, r1 += v.y, r2 += v.z;
     }
-    s_left[r] = make_uint4(0, 0, 0, 0);
-    if (s + 1 < a.nsc) {  // somebody to the right will want it
-      __stcg(&a.rowagg[(size_t)tile * kMaxBandRows + r], make_uint4(r0, r1, r2, 0));
-    }
+    if (s + 1 < a.nsc)  // somebody to the right will want it
+      st_unit(&a.rowagg[(size_t)tile * kMaxBandRows + r], r0, r1, r2, a.epoch);
   }
-  __syncthreads();
-  if (threadIdx.x == 0 && s + 1 < a.nsc) st_release(&a.flag_left[tile], a.epoch);
+  FOV_TRACE(3);
 
   // ---- left carry: add up the row sums of every CTA to the left in this band -----------------
-  for (int q = warp; q < s; q += NW) {
-    const uint32_t pt = tile - (uint32_t)s + (uint32_t)q;
-    if (lane == 0)
-      while (ld_acquire(&a.flag_left[pt]) != a.epoch && !a.debug_nowait) __nanosleep(40);
-    __syncwarp();
-    for (int r = lane; r < rows; r += 32) {
-      const uint4 v = __ldcg(&a.rowagg[(size_t)pt * kMaxBandRows + r]);
-      uint32_t *d = reinterpret_cast<uint32_t *>(&s_left[r]);
-      atomicAdd(d + 0, v.x);
-      atomicAdd(d + 1, v.y);
-      atomicAdd(d + 2, v.z);
+  // warp w takes CTAs w, w + NW, ...; lane r polls the units of rows r and r + 32
+  if (warp < s) {
+    uint32_t l[2][3] = {{0, 0, 0}, {0, 0, 0}};
+    for (int q = warp; q < s; q += NW) {
+      const uint4 *pu = a.rowagg + (size_t)(tile - (uint32_t)s + (uint32_t)q) * kMaxBandRows;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int r = lane + 32 * h;
+        if (r < rows) {
+          uint4 v = ld_unit(pu + r);
+          while (v.w != a.epoch) {
+            __nanosleep(20);
+            v = ld_unit(pu + r);
+          }
+          l[h][0] += v.x, l[h][1] += v.y, l[h][2] += v.z;
+        }
+      }
+    }
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int r = lane + 32 * h;
+      if (r < rows) {
+        uint32_t *d = reinterpret_cast<uint32_t *>(&s_left[r]);
+        atomicAdd(d + 0, l[h][0]);
+        atomicAdd(d + 1, l[h][1]);
+        atomicAdd(d + 2, l[h][2]);
+      }
     }
   }
   __syncthreads();
-  if (warp == 0) {
-    uint32_t l0 = 0, l1 = 0, l2 = 0;
-    for (int r = lane; r < rows; r += 32) {
-      const uint4 v = s_left[r];
-      l0 += v.x, l1 += v.y, l2 += v.z;
-    }
-    l0 = __reduce_add_sync(0xffffffffu, l0);
-    l1 = __reduce_add_sync(0xffffffffu, l1);
-    l2 = __reduce_add_sync(0xffffffffu, l2);
-    if (lane == 0) s_lsum = make_uint4(l0, l1, l2, 0);
-  }
-  __syncthreads();
+  FOV_TRACE(4);
 
   if (active) {
+    // ---- carry-in of each row (CTAs to the left + warps to the left) and its sum over the rows
+    uint4 *rc = s_rs + warp * kMaxBandRows;
+    uint32_t b0 = 0, b1 = 0, b2 = 0;
+    for (int r = lane; r < rows; r += 32) {
+      const uint4 c1 = rc[r], c2 = s_left[r];
+      const uint4 c = make_uint4(c1.x + c2.x, c1.y + c2.y, c1.z + c2.z, 0);
+      rc[r] = c;
+      b0 += c.x, b1 += c.y, b2 += c.z;
+    }
+    b0 = __reduce_add_sync(0xffffffffu, b0);
+    b1 = __reduce_add_sync(0xffffffffu, b1);
+    b2 = __reduce_add_sync(0xffffffffu, b2);  // also orders the rc[] writes before phase C
+
     // ---- band aggregate G(x) = everything this band adds to the SAT row below it -------------
     uint32_t gsum[12];
     {
-      uint32_t b0 = s_lsum.x, b1 = s_lsum.y, b2 = s_lsum.z;
-      for (int w = 0; w < warp; ++w) {
-        const uint4 v = s_wt[w];
-        b0 += v.x, b1 += v.y, b2 += v.z;
-      }
 #pragma unroll
-      for (int i = 0; i < 12; ++i) gsum[i] = acc[i];
+      for (int k = 0; k < 4; ++k)
+        gsum[3 * k + 0] = crb[k] & 0xffffu, gsum[3 * k + 1] = cg[k], gsum[3 * k + 2] = crb[k] >> 16;
 #pragma unroll
       for (int k = 1; k < 4; ++k)
 #pragma unroll
@@ -250,65 +278,56 @@ __global__ void __launch_bounds__(kMaxWarps * 32, MIN_CTAS) sat_onepass_kernel(c
     }
 
     // ---- column carry by decoupled look-back up the warp-strip column ------------------------
+    // A lane owns 4 units (12 words); each unit is followed on its own until it meets an
+    // inclusive value, so a predecessor caught between its AGG and INC stores is harmless.
+    uint32_t acc[12];
 #pragma unroll
     for (int i = 0; i < 12; ++i) acc[i] = 0;  // becomes T_b(x)
     const uint32_t col = tile * (uint32_t)NW + (uint32_t)warp;
     const uint32_t col_step = (uint32_t)a.n * (uint32_t)a.nsc * (uint32_t)NW;  // one band up
     const bool more_bands = b + 1 < a.nb;
+    uint4 *my_units = a.colagg + (size_t)col * 128 + lane;
     if (b > 0) {
-      if (more_bands) {
-        if (in_x) {
-          uint4 *d = reinterpret_cast<uint4 *>(a.colagg + (size_t)col * (kStripPx * 3)) + lane * 3;
-          __stcg(d + 0, make_uint4(gsum[0], gsum[1], gsum[2], gsum[3]));
-          __stcg(d + 1, make_uint4(gsum[4], gsum[5], gsum[6], gsum[7]));
-          __stcg(d + 2, make_uint4(gsum[8], gsum[9], gsum[10], gsum[11]));
-        }
-        __syncwarp();
-        if (lane == 0) st_release(&a.flag_col[col], (a.epoch << 2) | kAgg);
+      if (more_bands && in_x) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          st_unit(my_units + 32 * k, gsum[3 * k], gsum[3 * k + 1], gsum[3 * k + 2],
+                  (a.epoch << 2) | kAgg);
       }
-      int k = b - 1;
+      uint32_t open = in_x ? 0xfu : 0u;  // units still looking for an inclusive value
       uint32_t pc = col - col_step;
-      while (true) {
-        uint32_t st = 0;
-        if (lane == 0)
-          while (((st = ld_acquire(&a.flag_col[pc])) >> 2) != a.epoch && !a.debug_nowait)
-            __nanosleep(20);
-        if (a.debug_nowait) st = kInc;
-        st = __shfl_sync(0xffffffffu, st, 0);
-        if ((st & 3u) == kInc) {  // T_{k+1} = last SAT row of band k: final
-          if (in_x) {
-            const int yr = min((k + 1) * a.R, a.H) - 1;
-            const uint4 *p = reinterpret_cast<const uint4 *>(sat + ((size_t)yr * a.W + x0) * 3);
-            add12(acc, __ldcg(p), __ldcg(p + 1), __ldcg(p + 2));
+      while (__any_sync(0xffffffffu, open != 0)) {
+        const uint4 *pu = a.colagg + (size_t)pc * 128 + lane;
+        uint32_t pending = open;
+        while (pending) {
+          uint4 u[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            if (pending & (1u << k)) u[k] = ld_unit(pu + 32 * k);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            if ((pending & (1u << k)) && (u[k].w >> 2) == a.epoch) {
+              acc[3 * k + 0] += u[k].x, acc[3 * k + 1] += u[k].y, acc[3 * k + 2] += u[k].z;
+              pending &= ~(1u << k);
+              if ((u[k].w & 3u) == kInc) open &= ~(1u << k);
+            }
           }
-          break;
+          if (pending) __nanosleep(20);
         }
-        if (in_x) {
-          const uint4 *p =
-              reinterpret_cast<const uint4 *>(a.colagg + (size_t)pc * (kStripPx * 3)) + lane * 3;
-          add12(acc, __ldcg(p), __ldcg(p + 1), __ldcg(p + 2));
-        }
-        if (k == 0) break;  // T_0 = 0
-        --k;
-        pc -= col_step;
+        pc -= col_step;  // band 0 only ever publishes inclusive values: the walk ends there
       }
     }
-    if (more_bands) {
-      // publish the inclusive value = the tile's last SAT row (phase C rewrites the same words)
-      if (in_x) {
-        uint4 *d = reinterpret_cast<uint4 *>(sat + ((size_t)(y1 - 1) * a.W + x0) * 3);
-        __stcg(d + 0, make_uint4(acc[0] + gsum[0], acc[1] + gsum[1], acc[2] + gsum[2], acc[3] + gsum[3]));
-        __stcg(d + 1, make_uint4(acc[4] + gsum[4], acc[5] + gsum[5], acc[6] + gsum[6], acc[7] + gsum[7]));
-        __stcg(d + 2, make_uint4(acc[8] + gsum[8], acc[9] + gsum[9], acc[10] + gsum[10], acc[11] + gsum[11]));
-      }
-      __syncwarp();
-      if (lane == 0) st_release(&a.flag_col[col], (a.epoch << 2) | kInc);
+    if (more_bands && in_x) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        st_unit(my_units + 32 * k, acc[3 * k] + gsum[3 * k], acc[3 * k + 1] + gsum[3 * k + 1],
+                acc[3 * k + 2] + gsum[3 * k + 2], (a.epoch << 2) | kInc);
     }
+    FOV_TRACE(5);
 
     // ---- phase C: re-read the strip (L2), scan each row, accumulate down, write once ----------
-    const uint4 *rc = s_rs + warp * kMaxBandRows;  // exclusive prefix over the CTA's warps
     const int strip_px = min(kStripPx, a.W - strip * kStripPx);
-    uint8_t *my_stage = stage + (size_t)warp * kStageBufs * kRowBytes;
+    uint8_t *my_stage = stage + (size_t)warp * kBufs * kRowBytes;
     const uint64_t policy = pol_stream;
     int buf = 0;
     uint4 p[U];
@@ -327,34 +346,33 @@ __global__ void __launch_bounds__(kMaxWarps * 32, MIN_CTAS) sat_onepass_kernel(c
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         if (y + u < y1) {
-          uint32_t v[12];
-          unpack_px4(q[u], v);
-          if (lane == 0) {  // carry-in of this row: CTAs to the left + warps to the left
-            const uint4 c1 = rc[y + u - y0], c2 = s_left[y + u - y0];
-            v[0] += c1.x + c2.x, v[1] += c1.y + c2.y, v[2] += c1.z + c2.z;
-          }
+          // row prefix inside the 128-pixel strip in packed 16-bit fields (<= 128 * 255)
+          const uint32_t w[4] = {q[u].x, q[u].y, q[u].z, q[u].w};
+          uint32_t rb[4], g[4];
 #pragma unroll
-          for (int k = 1; k < 4; ++k)
+          for (int k = 0; k < 4; ++k)
+            rb[k] = w[k] & 0x00ff00ffu, g[k] = __byte_perm(w[k], 0, 0x4441);
 #pragma unroll
-            for (int c = 0; c < 3; ++c) v[3 * k + c] += v[3 * (k - 1) + c];
-          uint32_t i0 = v[9], i1 = v[10], i2 = v[11];
-          const uint32_t t0 = i0, t1 = i1, t2 = i2;
-          warp_scan3(i0, i1, i2, lane);
-          i0 -= t0, i1 -= t1, i2 -= t2;
+          for (int k = 1; k < 4; ++k) rb[k] += rb[k - 1], g[k] += g[k - 1];
+          uint32_t irb = rb[3], ig = g[3];
+          warp_scan2(irb, ig, lane);
+          irb -= rb[3], ig -= g[3];
+          const uint4 c = rc[y + u - y0];
+          const uint32_t cr = (irb & 0xffffu) + c.x, cgn = ig + c.y, cb = (irb >> 16) + c.z;
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
-            acc[3 * k + 0] += v[3 * k + 0] + i0;
-            acc[3 * k + 1] += v[3 * k + 1] + i1;
-            acc[3 * k + 2] += v[3 * k + 2] + i2;
+            acc[3 * k + 0] += (rb[k] & 0xffffu) + cr;
+            acc[3 * k + 1] += g[k] + cgn;
+            acc[3 * k + 2] += (rb[k] >> 16) + cb;
           }
           uint32_t *drow = sat + ((size_t)(y + u) * a.W) * 3;
+          uint8_t *sb = my_stage + (size_t)buf * kRowBytes;
+          uint4 *sd = reinterpret_cast<uint4 *>(sb + lane * 48);
           if (TMA_STORE) {
             // stage the 1536-byte row segment, then one bulk async store per row
-            uint8_t *sb = my_stage + (size_t)buf * kRowBytes;
             if (lane == 0)
-              asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(kStageBufs - 1) : "memory");
+              asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(kBufs - 1) : "memory");
             __syncwarp();
-            uint4 *sd = reinterpret_cast<uint4 *>(sb + lane * 48);
             sd[0] = make_uint4(acc[0], acc[1], acc[2], acc[3]);
             sd[1] = make_uint4(acc[4], acc[5], acc[6], acc[7]);
             sd[2] = make_uint4(acc[8], acc[9], acc[10], acc[11]);
@@ -367,12 +385,10 @@ __global__ void __launch_bounds__(kMaxWarps * 32, MIN_CTAS) sat_onepass_kernel(c
                   "r"(smem_u32(sb)), "r"(strip_px * 12), "l"(policy)
                   : "memory");
             }
-            buf = (buf + 1 == kStageBufs) ? 0 : buf + 1;
+            buf = (buf + 1 == kBufs) ? 0 : buf + 1;
           } else {
             // transpose through shared memory so that each store instruction of the warp covers
             // 512 contiguous bytes (lane-strided 48-byte stores run at ~60 % of this)
-            uint8_t *sb = my_stage + (size_t)buf * kRowBytes;
-            uint4 *sd = reinterpret_cast<uint4 *>(sb + lane * 48);
             sd[0] = make_uint4(acc[0], acc[1], acc[2], acc[3]);
             sd[1] = make_uint4(acc[4], acc[5], acc[6], acc[7]);
             sd[2] = make_uint4(acc[8], acc[9], acc[10], acc[11]);
@@ -396,16 +412,20 @@ __global__ void __launch_bounds__(kMaxWarps * 32, MIN_CTAS) sat_onepass_kernel(c
   }
 
   // ---- the last CTA to finish re-arms the ticket counter for the next launch ------------------
+  FOV_TRACE(6);
   __syncthreads();
+  FOV_TRACE(7);
   if (threadIdx.x == 0) {
-    __threadfence();
     if (atomicAdd(&a.counters[1], 1u) == a.total_tiles - 1) {
       a.counters[0] = 0;
       a.counters[1] = 0;
-      __threadfence();
     }
   }
 }
+
+#ifdef FOV360_SAT_TRACE
+long long *g_sat_trace = nullptr;
+#endif
 
 int env_int(const char *name, int dflt) {
   const char *e = getenv(name);
@@ -433,14 +453,12 @@ SatOnePassPlan sat_onepass_plan(int n, int W, int H) {
   const size_t tiles = (size_t)n * p.nb * p.nsc;
   auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
   p.off_counters = 0;
-  p.off_flag_left = 256;
-  p.off_flag_col = p.off_flag_left + al(tiles * 4);
-  p.off_rowagg = p.off_flag_col + al(tiles * p.NW * 4);
+  p.off_rowagg = 256;
   p.off_colagg = p.off_rowagg + al(tiles * kMaxBandRows * 16);
-  p.bytes = p.off_colagg + al(tiles * p.NW * kStripPx * 12);
-  // Flags are matched against a per-launch epoch, so they never need clearing between launches
-  // of one layout; the counters and both flag arrays must be zeroed when the layout changes.
-  p.clear_bytes = p.off_rowagg;
+  p.bytes = p.off_colagg + al(tiles * p.NW * 128 * 16);
+  // Every carry unit is tagged with the launch epoch, so nothing is cleared between launches of
+  // one layout; the whole scratch is zeroed when the layout changes (stale tags) or the epoch wraps.
+  p.clear_bytes = p.bytes;
   return p;
 }
 
@@ -472,19 +490,20 @@ cudaError_t launch_sat_onepass(const LaunchCtx &lc, int n, uint32_t *sat, size_t
   a.ns = p.ns;
   a.nsc = p.nsc;
   a.epoch = epoch;
-  static const int nowait = env_int("FOV360_SAT_DEBUG_NOWAIT", 0);
-  a.debug_nowait = nowait;
   a.total_tiles = (uint32_t)((size_t)n * p.nb * p.nsc);
+  static const int policy = env_int("FOV360_SAT_POLICY", 0);
+  a.policy = policy;
   a.counters = reinterpret_cast<uint32_t *>(base + p.off_counters);
-  a.flag_left = reinterpret_cast<uint32_t *>(base + p.off_flag_left);
   a.rowagg = reinterpret_cast<uint4 *>(base + p.off_rowagg);
-  a.flag_col = reinterpret_cast<uint32_t *>(base + p.off_flag_col);
-  a.colagg = reinterpret_cast<uint32_t *>(base + p.off_colagg);
+  a.colagg = reinterpret_cast<uint4 *>(base + p.off_colagg);
+#ifdef FOV360_SAT_TRACE
+  a.trace = g_sat_trace;
+#endif
 
   static const bool tma_store = env_int("FOV360_SAT_TMA_STORE", 0) != 0;
-  const size_t carry_smem = (size_t)(p.NW * kMaxBandRows + kMaxBandRows + kMaxWarps) * 16;
-  const size_t smem = carry_smem + (size_t)p.NW * kStageBufs * kRowBytes;
-  const int max_smem = (kMaxWarps * kMaxBandRows + kMaxBandRows + kMaxWarps) * 16 +
+  const size_t carry_smem = (size_t)(p.NW * kMaxBandRows + kMaxBandRows) * 16;
+  const size_t smem = carry_smem + (size_t)p.NW * (tma_store ? kStageBufs : 2) * kRowBytes;
+  const int max_smem = (kMaxWarps * kMaxBandRows + kMaxBandRows) * 16 +
                        kMaxWarps * kStageBufs * kRowBytes;
   KernelScope ks(lc, "sat_onepass");
   static const int variant = env_int("FOV360_SAT_VARIANT", 0);
@@ -497,9 +516,11 @@ cudaError_t launch_sat_onepass(const LaunchCtx &lc, int n, uint32_t *sat, size_t
   if (tma_store)
     FOV_LAUNCH(1, 3, 8, 4);
   else if (variant == 1)
-    FOV_LAUNCH(2, 4, 8, 2);
+    FOV_LAUNCH(2, 4, 8, 4);
   else if (variant == 2)
-    FOV_LAUNCH(2, 3, 16, 4);
+    FOV_LAUNCH(2, 5, 8, 4);
+  else if (variant == 3)
+    FOV_LAUNCH(2, 4, 16, 4);
   else
     FOV_LAUNCH(2, 3, 8, 4);
 #undef FOV_LAUNCH
