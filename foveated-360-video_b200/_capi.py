@@ -82,6 +82,9 @@ def load(build_if_stale: bool = True) -> C.CDLL:
     if _LIB is not None:
         return _LIB
     path = _build.LIB_PATH
+    override = os.environ.get("FOV360_LIB")  # development only: A/B runs of kernel variants
+    if override:
+        path, build_if_stale = override, False
     if build_if_stale:
         try:
             path = _build.build()

@@ -245,15 +245,26 @@ __device__ __forceinline__ uint32_t pack_rgb0(uint32_t c0, uint32_t c1, uint32_t
   return __byte_perm(__byte_perm(c0, c1, 0x0040u), c2, 0x5410u);  // c0.b0, c1.b0, c2.b0, 0
 }
 
-constexpr int kInterpPx = 4;      // consecutive pixels per lane: one 16-byte store per row
-constexpr int kInterpRows = 32;   // consecutive rows per warp: the x-axis work is done once
-constexpr int kInterpMaxCols = 136;  // widest reduced-column window a warp stages per row
+constexpr int kInterpPx = 4;         // consecutive pixels per lane: one 16-byte store per row
+#ifndef FOV360_INTERP_ROWS
+#define FOV360_INTERP_ROWS 32
+#endif
+constexpr int kInterpRows = FOV360_INTERP_ROWS;  // rows per warp: the x-axis work is done once
+constexpr int kInterpMaxCols = 136;  // widest reduced-column window the generic path stages
+#ifndef FOV360_INTERP_CHUNK
+#define FOV360_INTERP_CHUNK 4
+#endif
+constexpr int kInterpChunk = FOV360_INTERP_CHUNK;  // rows per pass of the periphery path
+constexpr int kInterpWarps = 4;      // warps per CTA, stacked vertically
+#ifndef FOV360_INTERP_MIN_CTAS
+#define FOV360_INTERP_MIN_CTAS 6
+#endif
 
-// Row descriptor, resolved by lane r for row y0 + r and broadcast by shuffle.
-struct RowSel {
-  int rows;   // first reduced row | second reduced row << 16 (equal when ty is 0 or 1)
-  float ty;   // vertical ratio
-  int yex;    // exact-hit reduced row, or -1 when this row is not an exact hit
+// Row descriptor, resolved by one lane per row, read back as one shared-memory broadcast.
+struct __align__(16) RowSel {
+  int off_lo, off_hi;  // word offsets of the two reduced rows (equal when ty is 0 or 1)
+  float ty;            // vertical ratio
+  int info;            // exact-hit reduced row (or -1) << 1 | "row pair differs from the row above"
 };
 
 template <int C>
@@ -261,23 +272,64 @@ __device__ __forceinline__ float vmix_channel(uint32_t a, uint32_t b, float ty) 
   return mix_rn(byte_to_float<C>(a), byte_to_float<C>(b), ty);
 }
 
+// One reduced-buffer tap pair of a column as floats: p and (q - p), the two operands of the
+// vertical mix that do not depend on the output row.
+struct TapPair {
+  float p[3], d[3];
+};
+
+__device__ __forceinline__ void convert_tap_pair(TapPair &t, uint32_t p, uint32_t q) {
+  t.p[0] = byte_to_float<0>(p), t.p[1] = byte_to_float<1>(p), t.p[2] = byte_to_float<2>(p);
+  t.d[0] = __fsub_rn(byte_to_float<0>(q), t.p[0]);
+  t.d[1] = __fsub_rn(byte_to_float<1>(q), t.p[1]);
+  t.d[2] = __fsub_rn(byte_to_float<2>(q), t.p[2]);
+}
+
+// mix(p, q, t) = p + (q - p) * t with every operation rounded separately (no FMA), matching the
+// oracle's scalar float arithmetic (:143-150); d = q - p.  With q == p (or t == 0) it returns p.
+__device__ __forceinline__ float lerp_rn(float p, float d, float t) {
+#ifdef FOV360_FUSED_LERP
+  return __fmaf_rn(d, t, p);  // <= 1 LSB after truncation, not bit-exact
+#else
+  return __fadd_rn(p, __fmul_rn(d, t));
+#endif
+}
+
+__device__ __forceinline__ uint32_t lerp_px(const float4 v, const float4 d, float t) {
+  return pack_rgb0(trunc_bits(lerp_rn(v.x, d.x, t)), trunc_bits(lerp_rn(v.y, d.y, t)),
+                   trunc_bits(lerp_rn(v.z, d.z, t)));
+}
+
 // interpolate_rect, one warp = 128 columns x kInterpRows rows.
 //
 // Everything that depends on x only (table entry, wrap, border fix-ups, clamped reduced columns,
-// ratio) is resolved once per lane; the kInterpRows y entries are resolved by one lane each.
-// The bilinear tap is separable exactly as the reference evaluates it - mix vertically at the two
-// columns, then mix horizontally - so per row a warp first forms the vertical mixes V[c] for the
-// window of reduced columns its 128 pixels touch (one per column, not two per pixel; in the
-// periphery a column serves ~4.6 pixels) in shared memory as floats, then every pixel is one
-// horizontal mix of two staged values.  A ratio of exactly 0 or 1 makes mix() return one operand
-// unchanged, so 1:1 (foveal) columns/rows are handled by selecting that operand: bit-identical,
-// no arithmetic.  Warps that are entirely inside the 1:1 column band skip the staging.
-__global__ void __launch_bounds__(256, 4) sat_interpolate_rect_kernel(const InterpArgs a,
-                                                                      const GazeBatch g) {
-  __shared__ float4 vstage[8][2][kInterpMaxCols];
+// ratio) is resolved once per lane; the y entries are resolved by one lane per row.  The bilinear
+// tap is separable exactly as the reference evaluates it - mix vertically at the two columns, then
+// mix horizontally.  A ratio of exactly 0 or 1 makes mix() return one operand unchanged, so those
+// taps select that operand (both taps become the selected row / column): bit-identical.
+//
+// The log-rectilinear map is 1:1 around the gaze and 6-10x compressed outside, on each axis, so a
+// warp falls into one of these cases:
+//  * all 128 columns 1:1: no horizontal mix.  Rows that are 1:1 too are copies, loaded four rows
+//    at a time; the others mix two reduced rows whose converted taps (p, q - p) stay in registers
+//    while the row pair repeats (6-10 output rows).
+//  * at most 32 reduced columns under the 128 pixels (the periphery): lane c owns window column c.
+//    Per chunk of rows, pass 1 requests every tap of the chunk, forms the vertical mix V[c] and
+//    D[c] = V[c+1] - V[c] in shared memory, pass 2 forms each pixel as V[lo] + D[lo] * tx.
+//    Neither pass waits on global memory or synchronises inside.
+//    A pixel that hits a sample on both axes is a copy of all 4 bytes of that sample (:67-72): its
+//    colour is what the mixes select anyway, so V carries the sample's 4th byte along.
+//  * anything else (the warp straddles the edge of the 1:1 band, an exact hit that is not the
+//    selected tap, the +-W seam): generic row-by-row paths.
+__global__ void __launch_bounds__(32 * kInterpWarps, FOV360_INTERP_MIN_CTAS)
+    sat_interpolate_rect_kernel(const InterpArgs a, const GazeBatch g) {
+  constexpr int kStage =
+      2 * (kInterpChunk * 32 > kInterpMaxCols ? kInterpChunk * 32 : kInterpMaxCols);
+  __shared__ float4 vstage[kInterpWarps][kStage];  // V and D of the column window
+  __shared__ RowSel rowsel[kInterpWarps][kInterpRows];
   const int lane = threadIdx.x, warp = threadIdx.y;
   const int x4 = (blockIdx.x * 32 + lane) * kInterpPx;
-  const int y0 = (blockIdx.y * 8 + warp) * kInterpRows;
+  const int y0 = (blockIdx.y * kInterpWarps + warp) * kInterpRows;
   const int f = blockIdx.z;
   if (y0 >= a.H) return;  // warp-uniform
   const int W = a.W, H = a.H, ow = a.ow, oh = a.oh;
@@ -288,7 +340,7 @@ __global__ void __launch_bounds__(256, 4) sat_interpolate_rect_kernel(const Inte
   // ---- x axis: once per lane ------------------------------------------------------------
   int xlo[kInterpPx], xhi[kInterpPx], xex[kInterpPx];
   float xr[kInterpPx];
-  bool all_deg = true;
+  bool all_deg = true, simple = true;
   int cmin = 0x7fffffff, cmax = -1;
 #pragma unroll
   for (int k = 0; k < kInterpPx; ++k) {
@@ -310,6 +362,7 @@ __global__ void __launch_bounds__(256, 4) sat_interpolate_rect_kernel(const Inte
     xr[k] = sx.ratio;
     xex[k] = sx.exact ? sx.exact_idx : -1;
     all_deg = all_deg && deg;
+    simple = simple && (xex[k] < 0 || (xex[k] == xlo[k] && xhi[k] == xlo[k]));
     cmin = min(cmin, min(xlo[k], xhi[k]));
     cmax = max(cmax, max(xlo[k], xhi[k]));
   }
@@ -318,18 +371,27 @@ __global__ void __launch_bounds__(256, 4) sat_interpolate_rect_kernel(const Inte
   cmax = __reduce_max_sync(0xffffffffu, cmax);
   const int ncols = cmax - cmin + 1;
 
-  // ---- y axis: lane r resolves row y0 + r --------------------------------------------------
-  RowSel mine;
-  {
-    const int y = min(y0 + (lane & (kInterpRows - 1)), H - 1);
+  // ---- y axis: one lane per row --------------------------------------------------------------
+#pragma unroll
+  for (int rr = 0; rr < kInterpRows; rr += 32) {
+    const int y = min(y0 + rr + lane, H - 1);
     const int dy = clampi(y - cyp, -H, H);
     const AxisSel sy = resolve_axis(load_entry(a.ly + (dy + H)), cyp, H, oh, false);
     const bool deg = sy.ratio == 0.0f || sy.ratio == 1.0f;
     const int sel = sy.ratio == 1.0f ? sy.hi : sy.lo;
-    mine.rows = deg ? (sel | (sel << 16)) : (sy.lo | (sy.hi << 16));
+    const int rlo = deg ? sel : sy.lo, rhi = deg ? sel : sy.hi;
+    const int yex = sy.exact ? sy.exact_idx : -1;
+    simple = simple && (yex < 0 || (yex == rlo && rhi == rlo));
+    const int pair = rlo | (rhi << 16);
+    const int above = __shfl_up_sync(0xffffffffu, pair, 1);
+    RowSel mine;
+    mine.off_lo = rlo * ow;
+    mine.off_hi = rhi * ow;
     mine.ty = sy.ratio;
-    mine.yex = sy.exact ? sy.exact_idx : -1;
+    mine.info = (yex << 1) | ((lane == 0 || above != pair) ? 1 : 0);
+    rowsel[warp][rr + lane] = mine;
   }
+  simple = __all_sync(0xffffffffu, simple);  // also orders the rowsel writes before the reads
 
   uint32_t *orow = reinterpret_cast<uint32_t *>(a.out + (size_t)f * a.out_stride) +
                    (size_t)y0 * W + x4;
@@ -348,70 +410,159 @@ __global__ void __launch_bounds__(256, 4) sat_interpolate_rect_kernel(const Inte
     }
   };
 
-  if (all_deg) {
-    // Every pixel of this warp maps onto a single reduced column: vertical mix (or copy) only.
-    for (int r = 0; r < nrows; ++r, orow += W) {
-      const int rows = __shfl_sync(0xffffffffu, mine.rows, r);
-      const float ty = __shfl_sync(0xffffffffu, mine.ty, r);
-      const int yex = __shfl_sync(0xffffffffu, mine.yex, r);
-      const uint32_t *ra = red + (size_t)(rows & 0xffff) * ow;
-      const uint32_t *rb = red + (size_t)(rows >> 16) * ow;
-      uint32_t px[kInterpPx];
-      if ((rows & 0xffff) == (rows >> 16)) {  // warp-uniform: the row is a copy of a reduced row
-        const uint32_t *rex = red + (size_t)max(yex, 0) * ow;
+  if (simple && all_deg) {
+    // ---- every pixel maps onto a single reduced column: vertical mix (or copy) only ----------
+    const uint32_t *col[kInterpPx];
+    uint32_t keep[kInterpPx];  // bytes an exact-hit row copies: all 4 where x is an exact hit too
+#pragma unroll
+    for (int k = 0; k < kInterpPx; ++k) {
+      col[k] = red + xlo[k];
+      keep[k] = xex[k] >= 0 ? 0xffffffffu : 0x00ffffffu;
+    }
+    TapPair tp[kInterpPx] = {};
+    int r = 0;
+    while (r < nrows) {
+      const RowSel rs = rowsel[warp][r];
+      if (rs.off_lo == rs.off_hi) {
+        // Copy rows (1:1 on both axes) come in long runs: four rows of loads in flight per batch.
+        int nb = 1;
+        RowSel b[4];
+        b[0] = rs;
+#pragma unroll
+        for (int j = 1; j < 4; ++j) {
+          b[j] = rowsel[warp][min(r + j, kInterpRows - 1)];
+          if (nb == j && r + j < nrows && b[j].off_lo == b[j].off_hi) nb = j + 1;
+        }
+        uint32_t px[4][kInterpPx];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (j < nb) {
+            const bool yhit = b[j].info >= 0;  // exact-hit row index is not -1
+#pragma unroll
+            for (int k = 0; k < kInterpPx; ++k)
+              px[j][k] = __ldg(col[k] + b[j].off_lo) & (yhit ? keep[k] : 0x00ffffffu);
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (j < nb) {
+            store_row(px[j]);
+            orow += W;
+          }
+        }
+        r += nb;
+      } else {
+        if (rs.info & 1) {  // warp-uniform: new reduced row pair
+#pragma unroll
+          for (int k = 0; k < kInterpPx; ++k)
+            convert_tap_pair(tp[k], __ldg(col[k] + rs.off_lo), __ldg(col[k] + rs.off_hi));
+        }
+        uint32_t px[kInterpPx];
 #pragma unroll
         for (int k = 0; k < kInterpPx; ++k)
-          px[k] = (yex >= 0 && xex[k] >= 0) ? __ldg(rex + xex[k])  // :67-72: all 4 bytes
-                                            : (__ldg(ra + xlo[k]) & 0x00ffffffu);
-      } else {
+          px[k] = pack_rgb0(trunc_bits(lerp_rn(tp[k].p[0], tp[k].d[0], rs.ty)),
+                            trunc_bits(lerp_rn(tp[k].p[1], tp[k].d[1], rs.ty)),
+                            trunc_bits(lerp_rn(tp[k].p[2], tp[k].d[2], rs.ty)));
+        store_row(px);
+        orow += W;
+        ++r;
+      }
+    }
+    return;
+  }
+
+  float4 *vs = vstage[warp];
+  if (simple && ncols <= 32) {
+    // ---- periphery: lane c owns window column c ---------------------------------------------
+    const float4 *pv[kInterpPx];
+    uint32_t keep[kInterpPx];
+#pragma unroll
+    for (int k = 0; k < kInterpPx; ++k) {
+      pv[k] = vs + (xlo[k] - cmin);
+      if (xhi[k] == xlo[k]) xr[k] = 0.0f;  // V + D * 0 = V: the selected column, exactly
+      keep[k] = xex[k] >= 0 ? 0xff000000u : 0u;
+    }
+    // lanes past the window repeat its last column: every V and D stays finite, and the D of the
+    // last column (0, or never multiplied by a non-zero tx) needs no special case
+    const uint32_t *rcol = red + cmin + min(lane, ncols - 1);
+    TapPair tp = {};
+    for (int r0 = 0; r0 < nrows; r0 += kInterpChunk) {
+      uint32_t rawp[kInterpChunk], rawq[kInterpChunk];
+#pragma unroll
+      for (int j = 0; j < kInterpChunk; ++j) {
+        const RowSel rs = rowsel[warp][min(r0 + j, kInterpRows - 1)];
+        rawp[j] = __ldg(rcol + rs.off_lo);
+        rawq[j] = __ldg(rcol + rs.off_hi);
+      }
+      __syncwarp();  // pass 2 of the previous chunk has read its V and D
+#pragma unroll
+      for (int j = 0; j < kInterpChunk; ++j) {
+        const RowSel rs = rowsel[warp][min(r0 + j, kInterpRows - 1)];
+        if (rs.info & 1) convert_tap_pair(tp, rawp[j], rawq[j]);  // warp-uniform
+        const float v0 = lerp_rn(tp.p[0], tp.d[0], rs.ty);
+        const float v1 = lerp_rn(tp.p[1], tp.d[1], rs.ty);
+        const float v2 = lerp_rn(tp.p[2], tp.d[2], rs.ty);
+        const float n0 = __shfl_down_sync(0xffffffffu, v0, 1);
+        const float n1 = __shfl_down_sync(0xffffffffu, v1, 1);
+        const float n2 = __shfl_down_sync(0xffffffffu, v2, 1);
+        const uint32_t alpha = rs.info >= 0 ? (rawp[j] & 0xff000000u) : 0u;  // exact-hit rows
+        vs[j * 32 + lane] = make_float4(v0, v1, v2, __uint_as_float(alpha));
+        vs[(kInterpChunk + j) * 32 + lane] =
+            make_float4(__fsub_rn(n0, v0), __fsub_rn(n1, v1), __fsub_rn(n2, v2), 0.f);
+      }
+      __syncwarp();
+#pragma unroll
+      for (int j = 0; j < kInterpChunk; ++j) {
+        uint32_t px[kInterpPx];
 #pragma unroll
         for (int k = 0; k < kInterpPx; ++k) {
-          const uint32_t p = __ldg(ra + xlo[k]), q = __ldg(rb + xlo[k]);
-          px[k] = pack_rgb0(trunc_bits(vmix_channel<0>(p, q, ty)),
-                            trunc_bits(vmix_channel<1>(p, q, ty)),
-                            trunc_bits(vmix_channel<2>(p, q, ty)));
+          const float4 v = pv[k][j * 32], d = pv[k][(kInterpChunk + j) * 32];
+          px[k] = lerp_px(v, d, xr[k]) | (__float_as_uint(v.w) & keep[k]);
+        }
+        if (r0 + j < nrows) {
+          store_row(px);
+          orow += W;
         }
       }
-      store_row(px);
     }
     return;
   }
 
   if (ncols <= kInterpMaxCols) {
-    // Stage the vertical mixes of the column window, then one horizontal mix per pixel.
-    int olo[kInterpPx], ohi[kInterpPx];
+    // ---- wider windows (the warp straddles the edge of the 1:1 band), exact hits off the
+    // selected taps: stage V and D row by row, patch exact hits from the reduced buffer --------
+    const float4 *pv[kInterpPx];
 #pragma unroll
     for (int k = 0; k < kInterpPx; ++k) {
-      olo[k] = xlo[k] - cmin;
-      ohi[k] = xhi[k] - cmin;
+      pv[k] = vs + (xlo[k] - cmin);
+      if (xhi[k] == xlo[k]) xr[k] = 0.0f;
     }
     for (int r = 0; r < nrows; ++r, orow += W) {
-      const int rows = __shfl_sync(0xffffffffu, mine.rows, r);
-      const float ty = __shfl_sync(0xffffffffu, mine.ty, r);
-      const int yex = __shfl_sync(0xffffffffu, mine.yex, r);
-      const uint32_t *ra = red + (size_t)(rows & 0xffff) * ow + cmin;
-      const uint32_t *rb = red + (size_t)(rows >> 16) * ow + cmin;
-      float4 *vs = vstage[warp][r & 1];
-      if ((rows & 0xffff) == (rows >> 16)) {  // warp-uniform
-        for (int c = lane; c < ncols; c += 32) {
-          const uint32_t p = __ldg(ra + c);
-          vs[c] = make_float4(byte_to_float<0>(p), byte_to_float<1>(p), byte_to_float<2>(p), 0.f);
-        }
-      } else {
-        for (int c = lane; c < ncols; c += 32) {
-          const uint32_t p = __ldg(ra + c), q = __ldg(rb + c);
-          vs[c] = make_float4(vmix_channel<0>(p, q, ty), vmix_channel<1>(p, q, ty),
-                              vmix_channel<2>(p, q, ty), 0.f);
+      const RowSel rs = rowsel[warp][r];
+      const uint32_t *ra = red + rs.off_lo + cmin, *rb = red + rs.off_hi + cmin;
+      __syncwarp();  // the previous row's pixels have been formed
+      // an iteration stages 31 columns; lane 31 only supplies V[c+1] to lane 30
+      for (int c0 = 0; c0 < ncols; c0 += 31) {
+        const int c = min(c0 + lane, ncols - 1);
+        TapPair t;
+        convert_tap_pair(t, __ldg(ra + c), __ldg(rb + c));
+        const float v0 = lerp_rn(t.p[0], t.d[0], rs.ty);
+        const float v1 = lerp_rn(t.p[1], t.d[1], rs.ty);
+        const float v2 = lerp_rn(t.p[2], t.d[2], rs.ty);
+        const float n0 = __shfl_down_sync(0xffffffffu, v0, 1);
+        const float n1 = __shfl_down_sync(0xffffffffu, v1, 1);
+        const float n2 = __shfl_down_sync(0xffffffffu, v2, 1);
+        if (lane < 31 && c0 + lane < ncols) {
+          vs[c] = make_float4(v0, v1, v2, 0.f);
+          vs[kInterpMaxCols + c] =
+              make_float4(__fsub_rn(n0, v0), __fsub_rn(n1, v1), __fsub_rn(n2, v2), 0.f);
         }
       }
       __syncwarp();
       uint32_t px[kInterpPx];
 #pragma unroll
-      for (int k = 0; k < kInterpPx; ++k) {
-        const float4 l = vs[olo[k]], rr = vs[ohi[k]];
-        px[k] = pack_rgb0(trunc_bits(mix_rn(l.x, rr.x, xr[k])), trunc_bits(mix_rn(l.y, rr.y, xr[k])),
-                          trunc_bits(mix_rn(l.z, rr.z, xr[k])));
-      }
+      for (int k = 0; k < kInterpPx; ++k) px[k] = lerp_px(pv[k][0], pv[k][kInterpMaxCols], xr[k]);
+      const int yex = rs.info >> 1;
       if (yex >= 0) {  // warp-uniform: pixels that hit a sample on both axes copy all 4 bytes
         const uint32_t *rex = red + (size_t)yex * ow;
 #pragma unroll
@@ -423,13 +574,12 @@ __global__ void __launch_bounds__(256, 4) sat_interpolate_rect_kernel(const Inte
     return;
   }
 
-  // Seam warps (the window spans the whole reduced width): gather every tap directly.
+  // ---- seam warps (the window spans the whole reduced width): gather every tap directly ------
   for (int r = 0; r < nrows; ++r, orow += W) {
-    const int rows = __shfl_sync(0xffffffffu, mine.rows, r);
-    const float ty = __shfl_sync(0xffffffffu, mine.ty, r);
-    const int yex = __shfl_sync(0xffffffffu, mine.yex, r);
-    const uint32_t *ra = red + (size_t)(rows & 0xffff) * ow;
-    const uint32_t *rb = red + (size_t)(rows >> 16) * ow;
+    const RowSel rs = rowsel[warp][r];
+    const float ty = rs.ty;
+    const int yex = rs.info >> 1;
+    const uint32_t *ra = red + rs.off_lo, *rb = red + rs.off_hi;
     const uint32_t *rex = red + (size_t)max(yex, 0) * ow;
     uint32_t px[kInterpPx];
 #pragma unroll
@@ -524,8 +674,8 @@ cudaError_t launch_sat_interpolate_rect(const LaunchCtx &lc, int n, uint8_t *out
   a.ow = ow;
   a.oh = oh;
   const dim3 grid((W + 32 * kInterpPx - 1) / (32 * kInterpPx),
-                  (H + 8 * kInterpRows - 1) / (8 * kInterpRows), n),
-      block(32, 8);
+                  (H + kInterpWarps * kInterpRows - 1) / (kInterpWarps * kInterpRows), n),
+      block(32, kInterpWarps);
   KernelScope ks(lc, "sat_interpolate_rect");
   sat_interpolate_rect_kernel<<<grid, block, 0, lc.stream>>>(a, gaze);
   return cudaGetLastError();
