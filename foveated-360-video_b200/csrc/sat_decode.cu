@@ -391,7 +391,6 @@ __global__ void __launch_bounds__(32 * kInterpWarps, FOV360_INTERP_MIN_CTAS)
     mine.info = (yex << 1) | ((lane == 0 || above != pair) ? 1 : 0);
     rowsel[warp][rr + lane] = mine;
   }
-  simple = __all_sync(0xffffffffu, simple);  // also orders the rowsel writes before the reads
 
   uint32_t *orow = reinterpret_cast<uint32_t *>(a.out + (size_t)f * a.out_stride) +
                    (size_t)y0 * W + x4;
@@ -399,6 +398,8 @@ __global__ void __launch_bounds__(32 * kInterpWarps, FOV360_INTERP_MIN_CTAS)
   const bool vec_ok = (x4 + kInterpPx <= W) && ((reinterpret_cast<uintptr_t>(orow) & 15) == 0) &&
                       ((W & 3) == 0);
   const int nrows = min(kInterpRows, H - y0);
+  // the fast paths below also assume one aligned 16-byte store per lane and row
+  simple = __all_sync(0xffffffffu, simple && vec_ok);  // (orders the rowsel writes, too)
 
   auto store_row = [&](const uint32_t (&px)[kInterpPx]) {
     if (vec_ok) {
@@ -485,31 +486,53 @@ __global__ void __launch_bounds__(32 * kInterpWarps, FOV360_INTERP_MIN_CTAS)
     // lanes past the window repeat its last column: every V and D stays finite, and the D of the
     // last column (0, or never multiplied by a non-zero tx) needs no special case
     const uint32_t *rcol = red + cmin + min(lane, ncols - 1);
+    uint4 *orow4 = reinterpret_cast<uint4 *>(orow);  // `simple` implies aligned 16-byte stores
     TapPair tp = {};
-    for (int r0 = 0; r0 < nrows; r0 += kInterpChunk) {
-      uint32_t rawp[kInterpChunk], rawq[kInterpChunk];
+    uint32_t rawp[kInterpChunk], rawq[kInterpChunk];
+    auto request = [&](int r0) {
 #pragma unroll
       for (int j = 0; j < kInterpChunk; ++j) {
         const RowSel rs = rowsel[warp][min(r0 + j, kInterpRows - 1)];
         rawp[j] = __ldg(rcol + rs.off_lo);
         rawq[j] = __ldg(rcol + rs.off_hi);
       }
-      __syncwarp();  // pass 2 of the previous chunk has read its V and D
+    };
+    auto stage_row = [&](int j, const RowSel rs) {
+      const float v0 = lerp_rn(tp.p[0], tp.d[0], rs.ty);
+      const float v1 = lerp_rn(tp.p[1], tp.d[1], rs.ty);
+      const float v2 = lerp_rn(tp.p[2], tp.d[2], rs.ty);
+      const float n0 = __shfl_down_sync(0xffffffffu, v0, 1);
+      const float n1 = __shfl_down_sync(0xffffffffu, v1, 1);
+      const float n2 = __shfl_down_sync(0xffffffffu, v2, 1);
+      const uint32_t alpha = rs.info >= 0 ? (rawp[j] & 0xff000000u) : 0u;  // exact-hit rows
+      vs[j * 32 + lane] = make_float4(v0, v1, v2, __uint_as_float(alpha));
+      vs[(kInterpChunk + j) * 32 + lane] =
+          make_float4(__fsub_rn(n0, v0), __fsub_rn(n1, v1), __fsub_rn(n2, v2), 0.f);
+    };
+    request(0);
+    for (int r0 = 0; r0 < nrows; r0 += kInterpChunk) {
+      RowSel rs[kInterpChunk];
+      int fresh_later = 0;
 #pragma unroll
       for (int j = 0; j < kInterpChunk; ++j) {
-        const RowSel rs = rowsel[warp][min(r0 + j, kInterpRows - 1)];
-        if (rs.info & 1) convert_tap_pair(tp, rawp[j], rawq[j]);  // warp-uniform
-        const float v0 = lerp_rn(tp.p[0], tp.d[0], rs.ty);
-        const float v1 = lerp_rn(tp.p[1], tp.d[1], rs.ty);
-        const float v2 = lerp_rn(tp.p[2], tp.d[2], rs.ty);
-        const float n0 = __shfl_down_sync(0xffffffffu, v0, 1);
-        const float n1 = __shfl_down_sync(0xffffffffu, v1, 1);
-        const float n2 = __shfl_down_sync(0xffffffffu, v2, 1);
-        const uint32_t alpha = rs.info >= 0 ? (rawp[j] & 0xff000000u) : 0u;  // exact-hit rows
-        vs[j * 32 + lane] = make_float4(v0, v1, v2, __uint_as_float(alpha));
-        vs[(kInterpChunk + j) * 32 + lane] =
-            make_float4(__fsub_rn(n0, v0), __fsub_rn(n1, v1), __fsub_rn(n2, v2), 0.f);
+        rs[j] = rowsel[warp][min(r0 + j, kInterpRows - 1)];
+        if (j > 0) fresh_later |= rs[j].info;
       }
+      __syncwarp();  // pass 2 of the previous chunk has read its V and D
+      // pass 1.  In the periphery a reduced row pair lasts 6-10 rows, so most chunks convert taps
+      // once (or not at all); the general form converts under a predicate in every row.
+      if (!(fresh_later & 1)) {  // warp-uniform
+        if (rs[0].info & 1) convert_tap_pair(tp, rawp[0], rawq[0]);
+#pragma unroll
+        for (int j = 0; j < kInterpChunk; ++j) stage_row(j, rs[j]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < kInterpChunk; ++j) {
+          if (rs[j].info & 1) convert_tap_pair(tp, rawp[j], rawq[j]);
+          stage_row(j, rs[j]);
+        }
+      }
+      if (r0 + kInterpChunk < nrows) request(r0 + kInterpChunk);  // in flight during pass 2
       __syncwarp();
 #pragma unroll
       for (int j = 0; j < kInterpChunk; ++j) {
@@ -519,10 +542,8 @@ __global__ void __launch_bounds__(32 * kInterpWarps, FOV360_INTERP_MIN_CTAS)
           const float4 v = pv[k][j * 32], d = pv[k][(kInterpChunk + j) * 32];
           px[k] = lerp_px(v, d, xr[k]) | (__float_as_uint(v.w) & keep[k]);
         }
-        if (r0 + j < nrows) {
-          store_row(px);
-          orow += W;
-        }
+        if (r0 + j < nrows) __stcs(orow4, make_uint4(px[0], px[1], px[2], px[3]));
+        orow4 += W / 4;
       }
     }
     return;
