@@ -460,9 +460,13 @@ int fov_sat_grid_export(fov_ctx *ctx, int16_t *host_grid, int ow, int oh, int W,
   return FOV_OK;
 }
 
-int fov_sat_sample_rect_batched(fov_ctx *ctx, int n, uint8_t *out, size_t out_stride, int ow,
-                                int oh, int out_linesize, const uint32_t *sat, size_t sat_stride,
-                                int W, int H, const float *gaze_xy) {
+namespace {
+// sample_rect for n frames.  `src` (optional) are the RGB0 frames the SATs were built from by this
+// library in the same call sequence: the kernel may read 1x1 boxes from them (identical bits).
+int sample_rect_batched(fov_ctx *ctx, int n, uint8_t *out, size_t out_stride, int ow, int oh,
+                        int out_linesize, const uint32_t *sat, size_t sat_stride, int W, int H,
+                        const float *gaze_xy, const uint8_t *src, size_t src_stride,
+                        int src_linesize) {
   FOV_REQUIRE_CTX(ctx);
   if (n <= 0 || !out || !sat || !gaze_xy || ow <= 0 || oh <= 0 || out_linesize < 4 * ow ||
       (out_linesize % 4) != 0 || ((uintptr_t)out % 4) != 0 || (out_stride % 4) != 0 ||
@@ -482,10 +486,19 @@ int fov_sat_sample_rect_batched(fov_ctx *ctx, int n, uint8_t *out, size_t out_st
                  ctx->lc(), m, out + (size_t)f0 * out_stride, out_stride, ow, oh, out_linesize,
                  reinterpret_cast<const uint32_t *>(reinterpret_cast<const uint8_t *>(sat) +
                                                     (size_t)f0 * sat_stride),
-                 sat_stride, W, H, grid->d_xedge, grid->d_yedge, gz),
+                 sat_stride, W, H, grid->d_xedge, grid->d_yedge, gz,
+                 src ? src + (size_t)f0 * src_stride : nullptr, src_stride, src_linesize),
              "sample_rect launch");
   }
   return FOV_OK;
+}
+}  // namespace
+
+int fov_sat_sample_rect_batched(fov_ctx *ctx, int n, uint8_t *out, size_t out_stride, int ow,
+                                int oh, int out_linesize, const uint32_t *sat, size_t sat_stride,
+                                int W, int H, const float *gaze_xy) {
+  return sample_rect_batched(ctx, n, out, out_stride, ow, oh, out_linesize, sat, sat_stride, W, H,
+                             gaze_xy, nullptr, 0, 0);
 }
 
 int fov_sat_sample_rect(fov_ctx *ctx, uint8_t *out, int ow, int oh, int out_linesize,
@@ -543,8 +556,12 @@ int fov_sat_foveate_batched(fov_ctx *ctx, int n, uint8_t *full_out, size_t full_
                             int ow, int oh, const float *gaze_xy) {
   int rc = fov_sat_encode_batched(ctx, n, sat, sat_stride, src, src_stride, W, H, linesize);
   if (rc) return rc;
-  rc = fov_sat_sample_rect_batched(ctx, n, reduced, red_stride, ow, oh, 4 * ow, sat, sat_stride, W,
-                                   H, gaze_xy);
+  // RGB0 frames with 4-byte aligned rows let sample_rect read its 1x1 boxes from the frame
+  static const bool no_hint = getenv("FOV360_SAMPLE_NO_SRC") != nullptr;
+  const bool hint = !no_hint && linesize / W == 4 && (linesize % 4) == 0 && ((uintptr_t)src % 4) == 0 &&
+                    (src_stride % 4) == 0;
+  rc = sample_rect_batched(ctx, n, reduced, red_stride, ow, oh, 4 * ow, sat, sat_stride, W, H,
+                           gaze_xy, hint ? src : nullptr, src_stride, linesize);
   if (rc) return rc;
   return fov_sat_interpolate_rect_batched(ctx, n, full_out, full_stride, W, H, reduced, red_stride,
                                           ow, oh, gaze_xy);

@@ -154,7 +154,9 @@ cudaError_t launch_sat_onepass(const LaunchCtx &lc, int n, uint32_t *sat, size_t
 cudaError_t launch_sat_sample_rect(const LaunchCtx &lc, int n, uint8_t *out, size_t out_stride, int ow,
                                    int oh, int out_linesize, const uint32_t *sat,
                                    size_t sat_stride, int W, int H, const int16_t *xedge,
-                                   const int16_t *yedge, const GazeBatch &gaze);
+                                   const int16_t *yedge, const GazeBatch &gaze,
+                                   const uint8_t *src = nullptr, size_t src_stride = 0,
+                                   int src_linesize = 0);
 cudaError_t launch_sat_interpolate_rect(const LaunchCtx &lc, int n, uint8_t *out, size_t out_stride,
                                         int W, int H, const uint8_t *red, size_t red_stride,
                                         int ow, int oh, const InterpEntry *lx,

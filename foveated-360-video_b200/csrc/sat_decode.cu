@@ -52,15 +52,24 @@ struct SampleArgs {
   const int16_t *xedge, *yedge;
   size_t out_stride, sat_stride;
   int ow, oh, o_linesize_px, W, H;
+  // Optional (fused encode+sample only): the RGB0 frames the SATs were just built from.  A 1x1 box
+  // sums to the source pixel itself, so the 1:1 region around the gaze reads 4 B per pixel from
+  // the frame instead of ~15 B of SAT corners - same bits by construction.
+  const uint32_t *src;
+  size_t src_stride;
+  int src_linesize_px;
 };
 
 constexpr int kSampleCols = 31;
+constexpr int kSampleWarps = 8;
 
 struct Rgb32 {
   uint32_t r, g, b;
 };
 
-__device__ __forceinline__ Rgb32 ld_sat(const uint32_t *p) {
+// One 12-byte SAT entry at a 32-bit word offset (a frame's SAT has fewer than 2^32 words).
+__device__ __forceinline__ Rgb32 ld_sat(const uint32_t *sat, uint32_t off) {
+  const uint32_t *p = sat + off;
   Rgb32 v;
   v.r = __ldg(p);
   v.g = __ldg(p + 1);
@@ -76,20 +85,58 @@ __device__ __forceinline__ Rgb32 shfl_down1(const Rgb32 v) {
   return o;
 }
 
+// Everything a reduced row contributes to its boxes, resolved once per CTA: the clamped SAT rows
+// of its top and bottom edge as word offsets, their distance, and two flags.
+struct __align__(16) SampleRow {
+  uint32_t top_off, bot_off;  // my * W * 3, py * W * 3
+  int py;                     // bottom SAT row
+  int dyf;                    // (py - my) << 2 | flags
+                              // 1: the row is sampled at all (:199-200, and j < oh)
+                              // 2: its top edge is the bottom edge of the row above
+};
+
+#ifndef FOV360_SAMPLE_MIN_CTAS
+#define FOV360_SAMPLE_MIN_CTAS 5
+#endif
 template <int kSampleRows>
-__global__ void __launch_bounds__(256) sat_sample_rect_kernel(const SampleArgs a,
-                                                              const GazeBatch g) {
-  const int lane = threadIdx.x;
+__global__ void __launch_bounds__(32 * kSampleWarps, kSampleRows == 4 ? FOV360_SAMPLE_MIN_CTAS : 1)
+    sat_sample_rect_kernel(const SampleArgs a,
+                                                                            const GazeBatch g) {
+  __shared__ SampleRow srow[kSampleWarps * kSampleRows];
+  const int lane = threadIdx.x, warp = threadIdx.y;
   const int i = blockIdx.x * kSampleCols + lane;
-  const int j0 = (blockIdx.y * 8 + threadIdx.y) * kSampleRows;
+  const int jb = blockIdx.y * kSampleWarps * kSampleRows;
   const int f = blockIdx.z;
-  if (j0 >= a.oh) return;  // warp-uniform
   const int W = a.W, H = a.H, ow = a.ow, oh = a.oh;
   const int cxp = gaze_px(g.xy[2 * f], W);
   const int cyp = gaze_px(g.xy[2 * f + 1], H);
-  const bool has_px = lane < kSampleCols && i < ow;
+  const uint32_t row_words = (uint32_t)W * 3u;
 
-  // x edges of this lane's pixel (lanes past the last pixel compute harmless in-range values)
+  // ---- y edges of the CTA's rows: one thread per row ------------------------------------------
+  {
+    const int t = warp * 32 + lane;
+    if (t < kSampleWarps * kSampleRows) {
+      const int j = jb + t;
+      const int y0 = cyp + a.yedge[min(j, oh)];      // grid[j][i+1].y    (:174-175)
+      const int y1 = cyp + a.yedge[min(j + 1, oh)];  // grid[j+1][i+1].y  (:172-173)
+      const bool y_in = (y1 >= 0 && y1 < H) || (y0 >= 0 && y0 < H);  // :199-200
+      const int py = clampi(y1, 1, H - 1);                            // :202, :204
+      const int my = clampi(y0, 0, py - 1);
+      SampleRow d;
+      d.top_off = (uint32_t)my * row_words;
+      d.bot_off = (uint32_t)py * row_words;
+      d.py = py;
+      d.dyf = ((py - my) << 2) | ((y_in && j < oh) ? 1 : 0) | ((my == clampi(y0, 1, H - 1)) ? 2 : 0);
+      srow[t] = d;
+    }
+  }
+  __syncthreads();
+  const int j0 = jb + warp * kSampleRows;
+  if (j0 >= oh) return;  // warp-uniform
+  const SampleRow *rows = srow + warp * kSampleRows;
+
+  // ---- x edges of this lane's pixel (lanes past the last pixel compute harmless in-range values)
+  const bool has_px = lane < kSampleCols && i < ow;
   const int ic = min(i, ow - 1);
   int px = cxp + a.xedge[ic + 1];  // grid[j+1][i+1].x  (:168-169)
   int mx = cxp + a.xedge[ic];      // grid[j+1][i].x    (:170-171)
@@ -107,60 +154,77 @@ __global__ void __launch_bounds__(256) sat_sample_rect_kernel(const SampleArgs a
   const int mx_next = __shfl_down_sync(0xffffffffu, mx, 1);
   const bool share = lane < 31 && i + 1 < ow && px == mx_next;
   const bool own_right = has_px && !share;
+  const bool live = has_px && x_in;
+  const uint32_t colL = (uint32_t)mx * 3u, colR = (uint32_t)px * 3u;
+  const uint32_t dx = (uint32_t)(px - mx);
+
+  SampleRow d[kSampleRows];
+#pragma unroll
+  for (int r = 0; r < kSampleRows; ++r) d[r] = rows[r];
+  uint32_t *orow = reinterpret_cast<uint32_t *>(a.out + (size_t)f * a.out_stride) +
+                   (size_t)j0 * a.o_linesize_px + i;
+
+  if (a.src != nullptr) {
+    // 1:1 warps: every live box is one pixel wide and every sampled row one pixel high.
+    bool unit = !live || dx == 1u;
+#pragma unroll
+    for (int r = 0; r < kSampleRows; ++r) unit = unit && (!(d[r].dyf & 1) || (d[r].dyf >> 2) == 1);
+    if (__all_sync(0xffffffffu, unit)) {
+      // box (mx, px] x (my, py] = the pixel (px, py): S(py,px) - S(my,px) - S(py,mx) + S(my,mx)
+      const uint32_t *sp = reinterpret_cast<const uint32_t *>(
+                               reinterpret_cast<const uint8_t *>(a.src) + (size_t)f * a.src_stride) + px;
+      uint32_t v[kSampleRows], o[kSampleRows];
+#pragma unroll
+      for (int r = 0; r < kSampleRows; ++r) {
+        const bool on = live && (d[r].dyf & 1);
+        v[r] = on ? __ldg(sp + (size_t)d[r].py * a.src_linesize_px) : 0u;
+        o[r] = on ? orow[(size_t)r * a.o_linesize_px] : 0u;
+      }
+#pragma unroll
+      for (int r = 0; r < kSampleRows; ++r)
+        if (live && (d[r].dyf & 1))
+          orow[(size_t)r * a.o_linesize_px] = (o[r] & 0xff000000u) | (v[r] & 0x00ffffffu);
+      return;
+    }
+  }
 
   const uint32_t *sat =
       reinterpret_cast<const uint32_t *>(reinterpret_cast<const uint8_t *>(a.sat) +
                                          (size_t)f * a.sat_stride);
-  const uint32_t *colL = sat + (size_t)mx * 3;
-  const uint32_t *colR = sat + (size_t)px * 3;
-  const size_t row_words = (size_t)W * 3;
 
-  // Gather the left corner of all kSampleRows+1 horizontal edges up front (27 loads in flight
-  // per lane).  Edge e is the bottom edge of row e-1 and, away from the frame border, the top
-  // edge of row e; it is fetched at the bottom-edge form of its coordinate (:202).
-  int yraw[kSampleRows + 1];
+  // Gather the left corner of all kSampleRows+1 horizontal edges up front.  Edge r+1 is the bottom
+  // edge of row r and, away from the frame border, the top edge of row r+1.
   Rgb32 L[kSampleRows + 1];
+  L[0] = ld_sat(sat, d[0].top_off + colL);
 #pragma unroll
-  for (int e = 0; e <= kSampleRows; ++e) {
-    yraw[e] = cyp + a.yedge[min(j0 + e, oh)];
-    const int ye = (e == 0) ? clampi(yraw[0], 0, H - 2) : clampi(yraw[e], 1, H - 1);
-    L[e] = ld_sat(colL + (size_t)ye * row_words);
-  }
+  for (int r = 0; r < kSampleRows; ++r) L[r + 1] = ld_sat(sat, d[r].bot_off + colL);
 
   // The store keeps byte 3 of the target pixel (`.xyz =`, :212): fetch the old pixels now too.
-  uint32_t *orow = reinterpret_cast<uint32_t *>(a.out + (size_t)f * a.out_stride) +
-                   (size_t)j0 * a.o_linesize_px + i;
   uint32_t old[kSampleRows];
 #pragma unroll
   for (int r = 0; r < kSampleRows; ++r)
-    old[r] = (has_px && x_in && j0 + r < oh) ? orow[(size_t)r * a.o_linesize_px] : 0u;
+    old[r] = (live && (d[r].dyf & 1)) ? orow[(size_t)r * a.o_linesize_px] : 0u;
 
 #pragma unroll
   for (int r = 0; r < kSampleRows; ++r, orow += a.o_linesize_px) {
-    if (j0 + r >= oh) break;  // warp-uniform
-    int py = yraw[r + 1];     // grid[j+1][i+1].y  (:172-173)
-    int my = yraw[r];         // grid[j][i+1].y    (:174-175)
-    const bool y_in = (py >= 0 && py < H) || (my >= 0 && my < H);  // :199-200
-    if (!y_in) continue;        // warp-uniform: the whole row keeps its contents
-    py = clampi(py, 1, H - 1);  // :202, :204  (== the coordinate L[r+1] was fetched at)
-    my = clampi(my, 0, py - 1);
-    const int fetched_top = (r == 0) ? clampi(yraw[0], 0, H - 2) : clampi(yraw[r], 1, H - 1);
+    if (!(d[r].dyf & 1)) continue;  // warp-uniform: the whole row keeps its contents
     Rgb32 tl = L[r];
-    if (my != fetched_top) tl = ld_sat(colL + (size_t)my * row_words);  // warp-uniform, borders
+    if (r > 0 && !(d[r].dyf & 2)) tl = ld_sat(sat, d[r].top_off + colL);  // warp-uniform, borders
     const Rgb32 bl = L[r + 1];
     Rgb32 tr = shfl_down1(tl);
     Rgb32 br = shfl_down1(bl);
     if (own_right) {  // seam / border lanes and the last column gather their own right corners
-      tr = ld_sat(colR + (size_t)my * row_words);
-      br = ld_sat(colR + (size_t)py * row_words);
+      tr = ld_sat(sat, d[r].top_off + colR);
+      br = ld_sat(sat, d[r].bot_off + colR);
     }
-    if (has_px && x_in) {
+    if (live) {
       uint32_t s0 = br.r - tr.r + tl.r - bl.r;  // :212-217
       uint32_t s1 = br.g - tr.g + tl.g - bl.g;
       uint32_t s2 = br.b - tr.b + tl.b - bl.b;
-      const uint32_t area = (uint32_t)((px - mx) * (py - my));  // :211
+      const uint32_t area = dx * (uint32_t)(d[r].dyf >> 2);  // :211
       if (area != 1u) {
-        const float rcp = __frcp_rn((float)area);
+        float rcp;  // ~1 ulp is plenty: udiv_exact corrects the quotient by one either way
+        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rcp) : "f"((float)area));
         s0 = udiv_exact(s0, area, rcp);
         s1 = udiv_exact(s1, area, rcp);
         s2 = udiv_exact(s2, area, rcp);
@@ -651,8 +715,12 @@ __global__ void __launch_bounds__(256) sat_decode_kernel(uint8_t *out, int out_l
 cudaError_t launch_sat_sample_rect(const LaunchCtx &lc, int n, uint8_t *out, size_t out_stride, int ow,
                                    int oh, int out_linesize, const uint32_t *sat,
                                    size_t sat_stride, int W, int H, const int16_t *xedge,
-                                   const int16_t *yedge, const GazeBatch &gaze) {
+                                   const int16_t *yedge, const GazeBatch &gaze,
+                                   const uint8_t *src, size_t src_stride, int src_linesize) {
   SampleArgs a;
+  a.src = reinterpret_cast<const uint32_t *>(src);
+  a.src_stride = src_stride;
+  a.src_linesize_px = src_linesize / 4;
   a.out = out;
   a.sat = sat;
   a.xedge = xedge;
@@ -669,8 +737,9 @@ cudaError_t launch_sat_sample_rect(const LaunchCtx &lc, int n, uint8_t *out, siz
     return e ? atoi(e) : 4;
   }();
   const int rpw = rows_per_warp == 8 ? 8 : 4;
-  const dim3 grid((ow + kSampleCols - 1) / kSampleCols, (oh + 8 * rpw - 1) / (8 * rpw), n),
-      block(32, 8);
+  const dim3 grid((ow + kSampleCols - 1) / kSampleCols,
+                  (oh + kSampleWarps * rpw - 1) / (kSampleWarps * rpw), n),
+      block(32, kSampleWarps);
   KernelScope ks(lc, "sat_sample_rect");
   if (rpw == 8)
     sat_sample_rect_kernel<8><<<grid, block, 0, lc.stream>>>(a, gaze);

@@ -502,9 +502,9 @@ cudaError_t launch_sat_onepass(const LaunchCtx &lc, int n, uint32_t *sat, size_t
 
   static const bool tma_store = env_int("FOV360_SAT_TMA_STORE", 0) != 0;
   const size_t carry_smem = (size_t)(p.NW * kMaxBandRows + kMaxBandRows) * 16;
-  const size_t smem = carry_smem + (size_t)p.NW * (tma_store ? kStageBufs : 2) * kRowBytes;
-  const int max_smem = (kMaxWarps * kMaxBandRows + kMaxBandRows) * 16 +
-                       kMaxWarps * kStageBufs * kRowBytes;
+  static const int pad_smem = env_int("FOV360_SAT_PAD_SMEM", 0);  // occupancy experiments
+  const size_t smem = carry_smem + (size_t)p.NW * (tma_store ? kStageBufs : 2) * kRowBytes + pad_smem;
+  const int max_smem = 200 * 1024;
   KernelScope ks(lc, "sat_onepass");
   static const int variant = env_int("FOV360_SAT_VARIANT", 0);
 #define FOV_LAUNCH(TMA, MINC, DEPTH, UU)                                                          \

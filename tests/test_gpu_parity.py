@@ -273,6 +273,33 @@ def test_batched_pipeline_matches_single_calls(dev, fov, oracle):
         assert max_lsb(got_full[f][..., :3], w[..., :3]) <= 1, f
 
 
+def test_fused_pipeline_unit_boxes_read_source(dev, fov, oracle):
+    """fov_sat_foveate_batched reads 1x1 boxes from the source frame instead of the SAT: same bits,
+    also with a non-zero 4th source byte, a prefilled reduced buffer and gazes on the borders."""
+    W, H = 1920, 1080
+    ow, oh = fov.reduced_dim(W), fov.reduced_dim(H)
+    gaze = np.array([[0.5, 0.5], [0.0, 0.0], [0.999, 0.999], [0.02, 0.97], [0.75, 0.31]], np.float32)
+    n = len(gaze)
+    rng = np.random.default_rng(5)
+    frames = rng.integers(0, 256, (n, H, W, 4), dtype=np.uint8)  # noise, random alpha
+    prefill = rng.integers(0, 256, (n, oh, ow, 4), dtype=np.uint8)
+    src = dev.m.upload(frames)
+    sat = dev.m.Buffer(n * W * H * 12)
+    red = dev.m.upload(prefill)
+    full = dev.m.Buffer(n * W * H * 4)
+    fov.FoveateFramesGPU(dev.m, n, full, W * H * 4, red, ow * oh * 4, sat, W * H * 12, src,
+                         W * H * 4, W, H, 4 * W, ow, oh, gaze)
+    got_red = dev.m.copy_to_host(np.empty((n, oh, ow, 4), np.uint8), red)
+    got_full = dev.m.copy_to_host(np.empty((n, H, W, 4), np.uint8), full)
+    for f in range(n):
+        s = oracle.sat_encode(frames[f])
+        r = oracle.sat_sample_rect(s, ow, oh, float(gaze[f, 0]), float(gaze[f, 1]),
+                                   out=prefill[f].copy())
+        assert np.array_equal(got_red[f], r), f
+        w = oracle.sat_interpolate_rect(r, W, H, float(gaze[f, 0]), float(gaze[f, 1]))
+        assert max_lsb(got_full[f], w) <= 1, f
+
+
 # --------------------------------------------------------------------------- ImageSampler ----
 @pytest.mark.parametrize("W,H,ow,oh", [(1920, 1080, 1072, 608), (640, 360, 368, 208)])
 def test_image_sampler_vs_oracle(dev, oracle, W, H, ow, oh):
