@@ -5,7 +5,10 @@
 namespace fov {
 
 constexpr int kStripPx = 128;             // pixels per warp strip (32 lanes x 4 px)
-constexpr int kStageBufs = 4;             // TMA-store ring depth per warp
+#ifndef FOV360_STAGE_BUFS
+#define FOV360_STAGE_BUFS 2
+#endif
+constexpr int kStageBufs = FOV360_STAGE_BUFS;             // TMA-store ring depth per warp
 constexpr int kRowBytes = kStripPx * 12;  // one SAT row segment of a warp strip
 
 __device__ __forceinline__ uint4 ldg_stream(const uint4 *p) {

@@ -122,10 +122,11 @@ __global__ void __launch_bounds__(kMaxWarps * 32, MIN_CTAS) sat_onepass_kernel(c
   const int warp = threadIdx.x >> 5;
   uint8_t *stage = smem;  // [NW][kBufs][kRowBytes]
   uint4 *s_rs = reinterpret_cast<uint4 *>(smem + (size_t)NW * kBufs * kRowBytes);
-  uint4 *s_left = s_rs + NW * kMaxBandRows;  // [kMaxBandRows] carry from the CTAs to the left
+  const int RS = a.R;                  // row stride of the per-warp row-sum table
+  uint4 *s_left = s_rs + NW * RS;      // [R] carry from the CTAs to the left
 
   if (threadIdx.x == 0) s_ticket = atomicAdd(&a.counters[0], 1u);
-  if (threadIdx.x < kMaxBandRows) s_left[threadIdx.x] = make_uint4(0, 0, 0, 0);
+  if ((int)threadIdx.x < RS) s_left[threadIdx.x] = make_uint4(0, 0, 0, 0);
   __syncthreads();
   const uint32_t tile = s_ticket;  // (band, frame, strip) order
   FOV_TRACE(0);
@@ -188,7 +189,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32, MIN_CTAS) sat_onepass_kernel(c
       }
     }
     if (lane < nr)
-      s_rs[warp * kMaxBandRows + (yc - y0) + lane] = make_uint4(krb & 0xffffu, kg, krb >> 16, 0);
+      s_rs[warp * RS + (yc - y0) + lane] = make_uint4(krb & 0xffffu, kg, krb >> 16, 0);
   }
   FOV_TRACE(1);
   __syncthreads();
@@ -199,8 +200,8 @@ __global__ void __launch_bounds__(kMaxWarps * 32, MIN_CTAS) sat_onepass_kernel(c
     const int r = threadIdx.x;
     uint32_t r0 = 0, r1 = 0, r2 = 0;
     for (int w = 0; w < NW; ++w) {
-      const uint4 v = s_rs[w * kMaxBandRows + r];
-      s_rs[w * kMaxBandRows + r] = make_uint4(r0, r1, r2, 0);
+      const uint4 v = s_rs[w * RS + r];
+      s_rs[w * RS + r] = make_uint4(r0, r1, r2, 0);
       r0 += v.x, r1 += v.y, r2 += v.z;
     }
     if (s + 1 < a.nsc)  // somebody to the right will want it
@@ -243,7 +244,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32, MIN_CTAS) sat_onepass_kernel(c
 
   if (active) {
     // ---- carry-in of each row (CTAs to the left + warps to the left) and its sum over the rows
-    uint4 *rc = s_rs + warp * kMaxBandRows;
+    uint4 *rc = s_rs + warp * RS;
     uint32_t b0 = 0, b1 = 0, b2 = 0;
     for (int r = lane; r < rows; r += 32) {
       const uint4 c1 = rc[r], c2 = s_left[r];
@@ -500,17 +501,21 @@ cudaError_t launch_sat_onepass(const LaunchCtx &lc, int n, uint32_t *sat, size_t
   a.trace = g_sat_trace;
 #endif
 
-  static const bool tma_store = env_int("FOV360_SAT_TMA_STORE", 0) != 0;
-  const size_t carry_smem = (size_t)(p.NW * kMaxBandRows + kMaxBandRows) * 16;
+  static const bool tma_store = env_int("FOV360_SAT_TMA_STORE", 1) != 0;
+  const size_t carry_smem = (size_t)(p.NW * p.R + p.R) * 16;
   static const int pad_smem = env_int("FOV360_SAT_PAD_SMEM", 0);  // occupancy experiments
   const size_t smem = carry_smem + (size_t)p.NW * (tma_store ? kStageBufs : 2) * kRowBytes + pad_smem;
   const int max_smem = 200 * 1024;
   KernelScope ks(lc, "sat_onepass");
   static const int variant = env_int("FOV360_SAT_VARIANT", 0);
+  static const int carveout = env_int("FOV360_SAT_CARVEOUT", -1);  // % of the L1/shared array
 #define FOV_LAUNCH(TMA, MINC, DEPTH, UU)                                                          \
   do {                                                                                             \
     cudaFuncSetAttribute(sat_onepass_kernel<TMA, MINC, DEPTH, UU>,                                 \
                          cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);                   \
+    if (carveout >= 0)                                                                             \
+      cudaFuncSetAttribute(sat_onepass_kernel<TMA, MINC, DEPTH, UU>,                               \
+                           cudaFuncAttributePreferredSharedMemoryCarveout, carveout);              \
     sat_onepass_kernel<TMA, MINC, DEPTH, UU><<<a.total_tiles, p.NW * 32, smem, lc.stream>>>(a);    \
   } while (0)
   if (tma_store)

@@ -1,4 +1,4 @@
-timeout 600 python -m pytest tests -m gpu -x -q 2>&1 | tail -5
-timeout 120 python tools/stage_bench.py --tag hint | grep "fps\|sample"
-FOV360_SAMPLE_NO_SRC=1 timeout 120 python tools/stage_bench.py --tag nohint| grep "fps\|sample"
-for v in s5 s6; do FOV360_LIB=tools/variants/libfov360_$v.so timeout 120 python tools/stage_bench.py --tag $v | grep "fps\|sample"; FOV360_SAMPLE_NO_SRC=1 FOV360_LIB=tools/variants/libfov360_$v.so timeout 120 python tools/stage_bench.py --tag ${v}nohint | grep "fps\|sample"; done
+timeout 120 python tools/stage_bench.py --tag b4 | grep "fps\|onepass"
+for v in b2 b3 b6; do FOV360_LIB=tools/variants/libfov360_$v.so timeout 120 python tools/stage_bench.py --tag $v | grep "onepass"; done
+FOV360_SAT_BAND_ROWS=64 timeout 120 python tools/stage_bench.py --tag band64 | grep "onepass"
+FOV360_SAT_VARIANT=1 timeout 120 python tools/stage_bench.py --tag var1 | grep "onepass"
