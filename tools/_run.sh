@@ -1,4 +1,4 @@
-timeout 120 python tools/stage_bench.py --tag b4 | grep "fps\|onepass"
-for v in b2 b3 b6; do FOV360_LIB=tools/variants/libfov360_$v.so timeout 120 python tools/stage_bench.py --tag $v | grep "onepass"; done
-FOV360_SAT_BAND_ROWS=64 timeout 120 python tools/stage_bench.py --tag band64 | grep "onepass"
-FOV360_SAT_VARIANT=1 timeout 120 python tools/stage_bench.py --tag var1 | grep "onepass"
+set -x
+timeout 900 python bench.py --steps 50 --warmup 3 > gpurun_out/bench_v5.json 2> gpurun_out/bench_v5.err
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_v5.csv python bench.py --steps 3 --warmup 3 > gpurun_out/ncu_bench_v5.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -c 3 -o gpurun_out/prof_r01_v5_all -f python tools/profile_step.py --batch 8 --steps 1 > gpurun_out/ncu_v5.log 2>&1
