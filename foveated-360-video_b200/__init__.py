@@ -14,6 +14,7 @@ from .host import (  # noqa: F401
     FovError,
     ImageSampler,
     OpenCLManager,
+    Projections,
     SATDecoder,
     SATEncoder,
     reduced_dim,

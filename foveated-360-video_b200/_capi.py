@@ -58,6 +58,8 @@ PROTOTYPES = {
     "fov_img_sample_logpolar": (_i, [_vp, _vp, _i, _i, _i, _vp, _i, _i, _i, _f, _f]),
     "fov_img_interpolate_logpolar": (_i, [_vp, _vp, _i, _i, _i, _vp, _i, _i, _i, _f, _f]),
     "fov_img_logpolar_blur": (_i, [_vp, _vp, _i, _i, _i, _vp]),
+    "fov_gnomonic": (_i, [_vp, _vp, _i, _i, _i, _vp, _i, _i, _i, _f, _f]),
+    "fov_sat_interpolate_gnomonic": (_i, [_vp, _vp, _i, _i, _vp, _i, _i, _i, _i, _f, _f, _f, _f]),
     "fov_reduced_dim": (_i, [_i]),
 }
 

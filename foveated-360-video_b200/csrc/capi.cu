@@ -567,6 +567,41 @@ int fov_sat_foveate_batched(fov_ctx *ctx, int n, uint8_t *full_out, size_t full_
                                           ow, oh, gaze_xy);
 }
 
+// ---- Projections ----------------------------------------------------------------------------
+
+int fov_gnomonic(fov_ctx *ctx, uint8_t *out, int tw, int th, int out_linesize, const uint8_t *src,
+                 int W, int H, int src_linesize, float cx, float cy) {
+  FOV_REQUIRE_CTX(ctx);
+  (void)out_linesize;  // never reach the reference kernel either (projections.cc:65-71)
+  (void)src_linesize;
+  if (!out || !src || tw <= 0 || th <= 0 || W <= 0 || H <= 0 || ((uintptr_t)out % 4) != 0 ||
+      ((uintptr_t)src % 4) != 0)
+    return fail(ctx, FOV_ERR_INVALID, "fov_gnomonic: invalid arguments");
+  DeviceGuard g(ctx);
+  FOV_CUDA(ctx, launch_gnomonic(ctx->lc(), out, tw, th, src, W, H, make_gnomonic_view(cx, cy)),
+           "gnomonic launch");
+  return FOV_OK;
+}
+
+int fov_sat_interpolate_gnomonic(fov_ctx *ctx, uint8_t *out, int tw, int th, const uint8_t *red,
+                                 int ow, int oh, int W, int H, float gaze_x, float gaze_y,
+                                 float view_x, float view_y) {
+  FOV_REQUIRE_CTX(ctx);
+  if (!out || !red || tw <= 0 || th <= 0 || ow <= 0 || oh <= 0 || W <= 0 || H <= 0 ||
+      ((uintptr_t)out % 4) != 0 || ((uintptr_t)red % 4) != 0)
+    return fail(ctx, FOV_ERR_INVALID, "fov_sat_interpolate_gnomonic: invalid arguments");
+  DeviceGuard g(ctx);
+  const InterpLut *lut = nullptr;
+  int rc = get_interp_lut(ctx, W, H, ow, oh, &lut);
+  if (rc) return rc;
+  FOV_CUDA(ctx,
+           launch_sat_interpolate_gnomonic(ctx->lc(), out, tw, th, red, ow, oh, W, H, lut->d_x,
+                                           lut->d_y, gaze_x, gaze_y,
+                                           make_gnomonic_view(view_x, view_y)),
+           "interpolate_gnomonic launch");
+  return FOV_OK;
+}
+
 // ---- ImageSampler ---------------------------------------------------------------------------
 
 int fov_img_grid_init(fov_ctx *ctx, int ow, int oh, int W, int H) {

@@ -180,4 +180,19 @@ cudaError_t launch_img_logpolar_grid_expand(const LaunchCtx &lc, int16_t *grid, 
                                             const float *radius, const float *cs,
                                             const float *sn);
 
+// Projections (projections.cu, sat_decode.cu).  Per-call constants of the inverse gnomonic map:
+// phi1 / lambda0 are exact IEEE double arithmetic narrowed to float (projections_program.cl:26,28);
+// the sine / cosine of phi1 are evaluated once on the host with the libm the parity oracle uses.
+struct GnomonicView {
+  float lambda0;             // (cx - 0.5) * 2 * PI
+  float sin_phi1, cos_phi1;  // of phi1 = (cy - 0.5) * PI
+};
+GnomonicView make_gnomonic_view(float cx, float cy);  // luts.cc: host libm, like the tables
+cudaError_t launch_gnomonic(const LaunchCtx &lc, uint8_t *out, int tw, int th, const uint8_t *src,
+                            int W, int H, const GnomonicView &view);
+cudaError_t launch_sat_interpolate_gnomonic(const LaunchCtx &lc, uint8_t *out, int tw, int th,
+                                            const uint8_t *red, int ow, int oh, int W, int H,
+                                            const InterpEntry *lx, const InterpEntry *ly,
+                                            float gaze_x, float gaze_y, const GnomonicView &view);
+
 }  // namespace fov

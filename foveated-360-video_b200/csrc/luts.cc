@@ -122,4 +122,16 @@ void build_logpolar_axes(int ow, int oh, std::vector<float> &radius, std::vector
   }
 }
 
+// Gnomonic viewport constants (projections_program.cl:25-28): (center - 0.5) is promoted to
+// double by the double literals 0.5 / PI and narrowed to float on assignment; sin/cos of the float.
+GnomonicView make_gnomonic_view(float cx, float cy) {
+  const double PI = 3.141592653589793;
+  const float phi1 = (float)((cy - 0.5) * PI);
+  GnomonicView v;
+  v.lambda0 = (float)((cx - 0.5) * 2.0 * PI);
+  v.sin_phi1 = sinf(phi1);
+  v.cos_phi1 = cosf(phi1);
+  return v;
+}
+
 }  // namespace fov

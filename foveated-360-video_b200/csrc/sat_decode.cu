@@ -9,6 +9,7 @@
 #include <cstdlib>
 
 #include "fov360_internal.h"
+#include "projection_common.cuh"
 
 namespace fov {
 namespace {
@@ -685,6 +686,59 @@ __global__ void __launch_bounds__(32 * kInterpWarps, FOV360_INTERP_MIN_CTAS)
 }
 
 // ---------------------------------------------------------------------------------------
+// interpolate_rect + gnomonic fused: the viewport rendered straight from the reduced buffer.
+//
+// out(i, j) = interpolate_rect(reduced)[gnomonic source pixel of (i, j)] without ever forming the
+// full-resolution frame (what a head-mounted client displays is a viewport,
+// so the 4*W*H-byte un-warped frame is pure traffic).  One thread per viewport pixel evaluates the
+// inverse gnomonic map (projection_common.cuh) and then exactly the per-pixel form of
+// interpolate_rect_kernel - table entry per axis, border fix-ups, exact-hit copy, vertical mixes
+// then the horizontal one - so the result equals the two reference kernels run back to back.
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) sat_interpolate_gnomonic_kernel(
+    uint32_t *__restrict__ out, int tw, int th, const InterpArgs a, float gx, float gy,
+    const GnomonicView view) {
+  const int i = blockIdx.x * 32 + threadIdx.x;
+  const int j = blockIdx.y * 8 + threadIdx.y;
+  if (i >= tw || j >= th) return;
+  const int W = a.W, H = a.H, ow = a.ow, oh = a.oh;
+  int x, y;
+  gnomonic_source(i, j, tw, th, W, H, view, x, y);
+  const int cxp = gaze_px(gx, W), cyp = gaze_px(gy, H);
+  bool wrapped = false;  // sat_decoder_interpolate_kernel.cl:26-33
+  if (x - cxp > W / 2) {
+    x -= W;
+    wrapped = true;
+  } else if (x - cxp < -(W / 2)) {
+    x += W;
+    wrapped = true;
+  }
+  const AxisSel sx =
+      resolve_axis(load_entry(a.lx + (clampi(x - cxp, -W, W) + W)), cxp, W, ow, wrapped);
+  const AxisSel sy = resolve_axis(load_entry(a.ly + (clampi(y - cyp, -H, H) + H)), cyp, H, oh, false);
+  const uint32_t *red = reinterpret_cast<const uint32_t *>(a.red);
+  uint32_t px;
+  if (sx.exact && sy.exact) {  // :67-72: all 4 bytes of the sample
+    px = __ldg(red + (size_t)sy.exact_idx * ow + sx.exact_idx);
+  } else {
+    // a ratio of exactly 0 or 1 selects one tap (mix() returns that operand unchanged)
+    const bool xdeg = sx.ratio == 0.0f || sx.ratio == 1.0f, ydeg = sy.ratio == 0.0f || sy.ratio == 1.0f;
+    const int xsel = sx.ratio == 1.0f ? sx.hi : sx.lo, ysel = sy.ratio == 1.0f ? sy.hi : sy.lo;
+    const int xlo = xdeg ? xsel : sx.lo, xhi = xdeg ? xsel : sx.hi;
+    const int ylo = ydeg ? ysel : sy.lo, yhi = ydeg ? ysel : sy.hi;
+    const uint32_t *ra = red + (size_t)ylo * ow, *rb = red + (size_t)yhi * ow;
+    const uint32_t tl = __ldg(ra + xlo), tr = __ldg(ra + xhi);
+    const uint32_t bl = __ldg(rb + xlo), br = __ldg(rb + xhi);
+    const float tx = sx.ratio, ty = sy.ratio;
+    px = pack_rgb0(
+        trunc_bits(mix_rn(vmix_channel<0>(tl, bl, ty), vmix_channel<0>(tr, br, ty), tx)),
+        trunc_bits(mix_rn(vmix_channel<1>(tl, bl, ty), vmix_channel<1>(tr, br, ty), tx)),
+        trunc_bits(mix_rn(vmix_channel<2>(tl, bl, ty), vmix_channel<2>(tr, br, ty), tx)));
+  }
+  out[(size_t)j * tw + i] = px;
+}
+
+// ---------------------------------------------------------------------------------------
 // decode: 1x1 boxes, exact inverse of the SAT.
 // ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) sat_decode_kernel(uint8_t *out, int out_linesize, int bpp,
@@ -768,6 +822,28 @@ cudaError_t launch_sat_interpolate_rect(const LaunchCtx &lc, int n, uint8_t *out
       block(32, kInterpWarps);
   KernelScope ks(lc, "sat_interpolate_rect");
   sat_interpolate_rect_kernel<<<grid, block, 0, lc.stream>>>(a, gaze);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_sat_interpolate_gnomonic(const LaunchCtx &lc, uint8_t *out, int tw, int th,
+                                            const uint8_t *red, int ow, int oh, int W, int H,
+                                            const InterpEntry *lx, const InterpEntry *ly,
+                                            float gaze_x, float gaze_y, const GnomonicView &view) {
+  InterpArgs a;
+  a.out = out;
+  a.red = red;
+  a.lx = lx;
+  a.ly = ly;
+  a.out_stride = 0;
+  a.red_stride = 0;
+  a.W = W;
+  a.H = H;
+  a.ow = ow;
+  a.oh = oh;
+  const dim3 grid((tw + 31) / 32, (th + 7) / 8), block(32, 8);
+  KernelScope ks(lc, "sat_interpolate_gnomonic");
+  sat_interpolate_gnomonic_kernel<<<grid, block, 0, lc.stream>>>(
+      reinterpret_cast<uint32_t *>(out), tw, th, a, gaze_x, gaze_y, view);
   return cudaGetLastError();
 }
 

@@ -311,6 +311,35 @@ class ImageSampler:
                                                        height, linesize, _ptr(source_buffer)))
 
 
+class Projections:
+    """projections.h:20-35: viewport rendering (inverse gnomonic projection)."""
+
+    def __init__(self, cl_manager: OpenCLManager | None = None):
+        self.m = cl_manager
+
+    def _need(self):
+        if self.m is None or not self.m.ctx:
+            raise FovError("Not initialized with OpenCL")
+
+    def GnomonicProjection(self, target_buffer, target_width, target_height, target_linesize,
+                           source_buffer, source_width, source_height, source_linesize, center_x,
+                           center_y):
+        self._need()
+        self.m._check(self.m.lib.fov_gnomonic(
+            self.m.ctx, _ptr(target_buffer), target_width, target_height, target_linesize,
+            _ptr(source_buffer), source_width, source_height, source_linesize, center_x, center_y))
+
+    def InterpolateGnomonicGPU(self, target_buffer, target_width, target_height, reduced_buffer,
+                               reduced_width, reduced_height, full_width, full_height, gaze_x,
+                               gaze_y, view_x, view_y):
+        """interpolate_rect + gnomonic in one kernel (no reference counterpart)."""
+        self._need()
+        self.m._check(self.m.lib.fov_sat_interpolate_gnomonic(
+            self.m.ctx, _ptr(target_buffer), target_width, target_height, _ptr(reduced_buffer),
+            reduced_width, reduced_height, full_width, full_height, gaze_x, gaze_y, view_x,
+            view_y))
+
+
 def reduced_dim(full_dim: int) -> int:
     """16*ceil(dim/1.8/16), run_satlogrectilinear.cc:113-114."""
     return int(_capi.load().fov_reduced_dim(int(full_dim)))

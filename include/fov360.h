@@ -191,6 +191,25 @@ int fov_img_interpolate_logpolar(fov_ctx *ctx, uint8_t *out, int out_width, int 
 int fov_img_logpolar_blur(fov_ctx *ctx, uint8_t *out, int width, int height, int linesize,
                           const uint8_t *src);
 
+/* ---- Projections (projections.h:20-35) ----------------------------------------------------- */
+
+/* Projections::GnomonicProjection (projections.cc:51-86; gnomonic_kernel,
+ * projections_program.cl:7-47): inverse gnomonic projection of an out_width x out_height viewport
+ * (fixed tangent-plane extent 6 x 3) centred on (center_x, center_y) in [0,1]^2 out of a
+ * src_width x src_height equirectangular frame.  Both buffers are dense arrays of 4-byte pixels
+ * (the kernel's uchar3); the linesize arguments are accepted and ignored like the reference's. */
+int fov_gnomonic(fov_ctx *ctx, uint8_t *out, int out_width, int out_height, int out_linesize,
+                 const uint8_t *src, int src_width, int src_height, int src_linesize,
+                 float center_x, float center_y);
+/* No reference counterpart: fov_sat_interpolate_rect followed by
+ * fov_gnomonic in one kernel - the viewport is rendered straight from the reduced buffer and the
+ * full-resolution frame is never formed.  (gaze_x, gaze_y) is the foveation centre the reduced
+ * buffer was sampled with, (view_x, view_y) the viewport centre. */
+int fov_sat_interpolate_gnomonic(fov_ctx *ctx, uint8_t *out, int out_width, int out_height,
+                                 const uint8_t *reduced, int red_width, int red_height,
+                                 int full_width, int full_height, float gaze_x, float gaze_y,
+                                 float view_x, float view_y);
+
 /* ---- parameters.h semantics ------------------------------------------------------------ */
 
 /* REDUCED_BUFFER_WIDTH/HEIGHT (parameters.h:8-9) for 1920x1080, and the runner's general rule

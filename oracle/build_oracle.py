@@ -34,6 +34,7 @@ CL_FILES = [
     "image_sampler_sample_rect_kernel.cl",
     "image_sampler_sample_logpolar_kernel.cl",
     "image_sampler_interpolate_kernel.cl",
+    "projections_program.cl",
 ]
 
 # -ffp-contract=off: mix() and the transform formulas must round every float

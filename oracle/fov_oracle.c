@@ -500,6 +500,42 @@ void orc_img_logpolar_blur(uint8_t *out, int ow, int oh, int linesize, const uin
 }
 
 /* FNV-1a 64-bit over a raw buffer: the hash the golden fixtures are keyed on. */
+/* ---- Projections (section 8(f) rank 3) -------------------------------------------------- */
+
+/* gnomonic_kernel, projections_program.cl:7-47: inverse gnomonic projection of a tw x th
+ * viewport (fixed tangent-plane extent 6 x 3) centred on `center` out of a W x H equirectangular
+ * frame; both buffers are dense uchar3 arrays (4-byte pixels), the whole 4-byte pixel is copied.
+ * Typing follows OpenCL C: the #define'd PI / PI_2 are double literals, so phi1, lambda0, the two
+ * fmod wraps and the final divisions are evaluated in double and narrowed to float on assignment;
+ * everything else is float (sqrtf, atanf, sinf, cosf, asinf, atan2f). */
+void orc_gnomonic(uint8_t *out, int tw, int th, const uint8_t *src, int W, int H, float cx,
+                  float cy) {
+  const double PI = 3.141592653589793, PI_2 = 1.5707963267948966;
+  const uint32_t *s32 = (const uint32_t *)src;
+  uint32_t *o32 = (uint32_t *)out;
+#pragma omp parallel for schedule(static) num_threads(NT)
+  for (int j = 0; j < th; ++j) {
+    for (int i = 0; i < tw; ++i) {
+      const float u = (float)i / tw, v = (float)j / th;  /* :21 */
+      const float x = 6.0f * (u - 0.5f), y = 3.0f * (v - 0.5f); /* :19, :22-23 */
+      const float phi1 = (float)((cy - 0.5) * PI);          /* :26 */
+      const float lambda0 = (float)((cx - 0.5) * 2.0 * PI); /* :28 */
+      const float rho = sqrtf(x * x + y * y);
+      const float c = atanf(rho);
+      float phi = asinf(cosf(c) * sinf(phi1) + (y * sinf(c) * cosf(phi1)) / rho); /* :31 */
+      float lambda = lambda0 + atan2f(x * sinf(c), (rho * cosf(phi1) * cosf(c) -
+                                                    y * sinf(phi1) * sinf(c))); /* :32-34 */
+      phi = (float)fmod(phi + PI_2 + 10 * PI, 2 * PI);     /* :35 */
+      lambda = (float)fmod(lambda + PI + 10 * PI, 2 * PI); /* :36 */
+      float su = (float)(lambda / (2.0 * PI)), sv = (float)(phi / (PI)); /* :37 */
+      su = fminf(fmaxf(su, 0.0f), 0.999f); /* :38: clamp = fmin(fmax()), a NaN becomes 0 */
+      sv = fminf(fmaxf(sv, 0.0f), 0.999f);
+      const int sc = (int)(sv * H) * W + (int)(su * W); /* :40-41 */
+      o32[(size_t)j * tw + i] = s32[sc];                /* :43-44 */
+    }
+  }
+}
+
 uint64_t orc_fnv1a64(const uint8_t *p, size_t n) {
   uint64_t h = 0xcbf29ce484222325ull;
   for (size_t i = 0; i < n; ++i) {

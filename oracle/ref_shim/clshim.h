@@ -57,7 +57,15 @@ static inline int2 convert_int2(short2 s) { return int2((int)s.x, (int)s.y); }
 
 struct float2 {
   float x, y;
+  float2() : x(0), y(0) {}
+  // OpenCL converts each scalar initialiser to float; one scalar is replicated.
+  template <class A>
+  explicit float2(A s) : x((float)s), y((float)s) {}
+  template <class A, class B>
+  float2(A a, B b) : x((float)a), y((float)b) {}
 };
+static inline float2 operator*(float2 a, float2 b) { return float2(a.x * b.x, a.y * b.y); }
+static inline float2 operator-(float2 a, float2 b) { return float2(a.x - b.x, a.y - b.y); }
 
 struct uint3 {
   uint x, y, z;
@@ -128,13 +136,18 @@ static inline float3 mix(float3 a, float3 b, float t) {
 static inline int clamp(int v, int lo, int hi) { return std::min(std::max(v, lo), hi); }
 static inline uint clamp(uint v, uint lo, uint hi) { return std::min(std::max(v, lo), hi); }
 static inline float clamp(float v, float lo, float hi) { return std::fmin(std::fmax(v, lo), hi); }
+static inline float2 clamp(float2 v, float2 lo, float2 hi) {
+  return float2(clamp(v.x, lo.x, hi.x), clamp(v.y, lo.y, hi.y));
+}
 static inline int min(int a, int b) { return a < b ? a : b; }
 static inline int max(int a, int b) { return a > b ? a : b; }
 static inline float max(float a, float b) { return std::fmax(a, b); }
 static inline float min(float a, float b) { return std::fmin(a, b); }
 
 using std::abs;
+using std::asin;
 using std::atan;
+using std::atan2;
 using std::ceil;
 using std::cos;
 using std::exp;

@@ -38,6 +38,9 @@ namespace ref_img_lp {
 namespace ref_img_itp {
 #include "image_sampler_interpolate_kernel.cl.inc"
 }
+namespace ref_proj {  // last: its #define PI / PI_2 / DEG2RAD / RAD2DEG are not namespaced
+#include "projections_program.cl.inc"
+}
 
 namespace {
 
@@ -196,4 +199,15 @@ void ref_img_logpolar_blur(uint8_t *out, int ow, int oh, int linesize, const uin
   });
 }
 
+// Projections::GnomonicProjection, projections.cc:51-86 (8x8 work-groups over the viewport;
+// the linesize arguments never reach the kernel).
+void ref_gnomonic(uint8_t *out, int tw, int th, const uint8_t *src, int W, int H, float cx,
+                  float cy) {
+  float2 center = {cx, cy};
+  ndrange2(roundup8(tw), roundup8(th), [&] {
+    ref_proj::gnomonic_kernel(reinterpret_cast<uchar3 *>(out), tw, th,
+                              reinterpret_cast<uchar3 *>(const_cast<uint8_t *>(src)), W, H,
+                              center);
+  });
+}
 }  // extern "C"

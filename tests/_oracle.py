@@ -83,6 +83,7 @@ class Oracle:
             "img_interpolate_logpolar", _u8p, _i, _i, _u8p, _i, _i, _f, _f
         )
         self._img_logpolar_blur = sig("img_logpolar_blur", _u8p, _i, _i, _i, _u8p)
+        self._gnomonic = sig("gnomonic", _u8p, _i, _i, _u8p, _i, _i, _f, _f)
         if kind == "port":
             self._sat_grid_edges = sig("sat_grid_edges", _i16p, _i16p, _i, _i, _i, _i)
             self._fnv = sig("fnv1a64", C.c_void_p, C.c_size_t, res=C.c_uint64)
@@ -171,6 +172,14 @@ class Oracle:
         if out is None:
             out = np.zeros((H, W, 4), np.uint8)
         self._img_interpolate_logpolar(out, W, H, np.ascontiguousarray(reduced), ow, oh, cx, cy)
+        return out
+
+    def gnomonic(self, frame, tw, th, cx, cy, out=None) -> np.ndarray:
+        """Viewport tw x th out of a dense 4-byte-pixel equirect frame (projections.cc:51-86)."""
+        H, W, _ = frame.shape
+        if out is None:
+            out = np.zeros((th, tw, 4), np.uint8)
+        self._gnomonic(out, tw, th, np.ascontiguousarray(frame), W, H, cx, cy)
         return out
 
     def img_logpolar_blur(self, reduced, out=None) -> np.ndarray:

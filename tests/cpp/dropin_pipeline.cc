@@ -12,6 +12,7 @@
 
 #include "fov360/image_sampler.h"
 #include "fov360/parameters.h"
+#include "fov360/projections.h"
 #include "fov360/sat_decoder.h"
 #include "fov360/sat_encoder.h"
 
@@ -49,6 +50,7 @@ int main(int argc, char **argv) {
   SATEncoder sat_encoder(&cl_manager);
   SATDecoder sat_decoder(&cl_manager);
   ImageSampler image_sampler(&cl_manager);
+  Projections projections(&cl_manager);
   CodecCtxStub codec_ctx{W, H};
 
   cl::Buffer cl_source_buffer(cl_manager.context, CL_MEM_READ_WRITE, (size_t)linesize * H);
@@ -56,6 +58,9 @@ int main(int argc, char **argv) {
   cl::Buffer cl_out_buffer(cl_manager.context, CL_MEM_READ_WRITE, (size_t)out_linesize * oh);
   cl::Buffer cl_full_buffer(cl_manager.context, CL_MEM_READ_WRITE, (size_t)linesize * H);
   cl::Buffer cl_lp_buffer(cl_manager.context, CL_MEM_READ_WRITE, (size_t)out_linesize * oh);
+  const int vw = 960, vh = 540;  // viewport of the gnomonic golden vectors
+  cl::Buffer cl_view_buffer(cl_manager.context, CL_MEM_READ_WRITE, (size_t)4 * vw * vh);
+  cl::Buffer cl_view2_buffer(cl_manager.context, CL_MEM_READ_WRITE, (size_t)4 * vw * vh);
 
   std::vector<uint8_t> reduced((size_t)out_linesize * oh, 0), full((size_t)linesize * H, 0),
       logpolar((size_t)out_linesize * oh, 0);
@@ -75,6 +80,15 @@ int main(int argc, char **argv) {
   image_sampler.SampleFrameLogPolarGPU(cl_lp_buffer(), ow, oh, out_linesize, cl_source_buffer(), W,
                                        H, linesize, cx, cy);
 
+  // client side, projections.cc:51-86: viewport out of the un-warped frame, and the fused form
+  projections.GnomonicProjection(cl_view_buffer(), vw, vh, 4 * vw, cl_full_buffer(), W, H, linesize,
+                                 cx, cy);
+  projections.InterpolateGnomonicGPU(cl_view2_buffer(), vw, vh, cl_out_buffer(), ow, oh, W, H, cx, cy,
+                                     cx, cy);
+  std::vector<uint8_t> view((size_t)4 * vw * vh), view2((size_t)4 * vw * vh);
+  cl::copy(cl_manager.command_queue, cl_view_buffer, view.begin(), view.end());
+  cl::copy(cl_manager.command_queue, cl_view2_buffer, view2.begin(), view2.end());
+
   cl::copy(cl_manager.command_queue, cl_sat_buffer, sat.begin(), sat.end());
   cl::copy(cl_manager.command_queue, cl_out_buffer, reduced.begin(), reduced.end());
   cl::copy(cl_manager.command_queue, cl_full_buffer, full.begin(), full.end());
@@ -82,11 +96,11 @@ int main(int argc, char **argv) {
 
   printf("{\"W\": %d, \"H\": %d, \"ow\": %d, \"oh\": %d, \"sat\": \"%016llx\", "
          "\"reduced_zero\": \"%016llx\", \"interp\": \"%016llx\", \"logpolar\": \"%016llx\", "
-         "\"launches\": %llu}\n",
+         "\"view_equal\": %d, \"launches\": %llu}\n",
          W, H, ow, oh, (unsigned long long)fnv1a64(sat.data(), sat.size() * 4),
          (unsigned long long)fnv1a64(reduced.data(), reduced.size()),
          (unsigned long long)fnv1a64(full.data(), full.size()),
-         (unsigned long long)fnv1a64(logpolar.data(), logpolar.size()),
+         (unsigned long long)fnv1a64(logpolar.data(), logpolar.size()), (int)(view == view2),
          (unsigned long long)fov_ctx_launch_count(cl_manager.handle()));
   return 0;
 }

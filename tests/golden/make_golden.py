@@ -13,7 +13,9 @@ the reference's arithmetic.  Outputs:
 * golden.json  - FNV-1a-64 hashes / counts / probe pixels of every hot-path stage on seeded
                  synthetic frames at 1080p and 4K plus grid hashes up to 8K;
 * small.npz    - complete input/output arrays of a 96x64 case (every stage), small enough to diff
-                 element-wise.
+                 element-wise;
+* gnomonic_small.npz, gnomonic.json - Projections::GnomonicProjection viewports (complete arrays of
+                 a 192x96 frame, hashes at 1080p).
 """
 from __future__ import annotations
 
@@ -113,6 +115,29 @@ def main() -> None:
         arrays["interp_logpolar_%d" % k] = ref.img_interpolate_logpolar(lp, W, H, cx, cy)
     np.savez_compressed(os.path.join(HERE, "small.npz"), **arrays)
     print("wrote golden.json and small.npz")
+    gnomonic_vectors(ref)
+
+
+GNOMONIC_VIEWS = [(0.5, 0.5), (0.1, 0.9), (0.0, 0.0), (1.0, 1.0), (0.73, 0.31), (0.98, 0.5)]
+
+
+def gnomonic_vectors(ref) -> None:
+    """Projections::GnomonicProjection: complete viewports of a small frame + hashes at 1080p."""
+    W, H, tw, th = 192, 96, 80, 48
+    frame = O.lcg_frame(W, H, 31337)
+    frame[..., 3] = (np.arange(W * H, dtype=np.uint32) % 251).reshape(H, W).astype(np.uint8)  # 4th byte travels
+    arrays = {"frame": frame, "views": np.array(GNOMONIC_VIEWS, np.float32)}
+    for k, (cx, cy) in enumerate(GNOMONIC_VIEWS):
+        arrays["view_%d" % k] = ref.gnomonic(frame, tw, th, cx, cy)
+    np.savez_compressed(os.path.join(HERE, "gnomonic_small.npz"), **arrays)
+    big = O.lcg_frame(1920, 1080, 12345)
+    gold = {"generator": "oracle/_ref/libfovref.so (projections_program.cl, g++ shim)",
+            "W": 1920, "H": 1080, "seed": 12345, "tw": 960, "th": 540,
+            "views": [{"cx": cx, "cy": cy, "hash": h(ref.gnomonic(big, 960, 540, cx, cy))}
+                      for cx, cy in GNOMONIC_VIEWS]}
+    with open(os.path.join(HERE, "gnomonic.json"), "w") as fh:
+        json.dump(gold, fh, indent=1)
+    print("wrote gnomonic_small.npz and gnomonic.json")
 
 
 if __name__ == "__main__":

@@ -42,4 +42,5 @@ def test_dropin_call_sequence_matches_golden(fov, golden):
     assert got["interp"] == g["interp"]
     lp = [x for x in golden["logpolar"][0]["gaze"] if (x["cx"], x["cy"]) == (g["cx"], g["cy"])][0]
     assert got["logpolar"] == lp["logpolar"]
-    assert got["launches"] >= 4
+    assert got["view_equal"] == 1  # Projections: fused viewport == interpolate + gnomonic
+    assert got["launches"] >= 6

@@ -300,6 +300,60 @@ def test_fused_pipeline_unit_boxes_read_source(dev, fov, oracle):
         assert max_lsb(got_full[f], w) <= 1, f
 
 
+# ---------------------------------------------------------------------------- Projections ----
+def _gather_mismatch(got, want, src):
+    """Pixels where two gathers differ, and whether each differing pixel is still a copy of a source
+    pixel next to the oracle's (a 1-ulp libm difference moves a truncated index by one)."""
+    bad = (got != want).any(axis=2)
+    return int(bad.sum())
+
+
+@pytest.mark.parametrize("W,H,tw,th", [(1920, 1080, 960, 540), (3840, 1920, 1280, 720)])
+def test_gnomonic_vs_oracle(dev, fov, oracle, W, H, tw, th):
+    """fov_gnomonic against the restatement of gnomonic_kernel.  The index is a truncation of a
+    chain of seven float transcendentals: the device evaluates them correctly rounded, glibc's
+    float versions are within 1 ulp, so a few pixels per million may land on the neighbouring
+    source pixel.  Contract: >= 99.9 % of the pixels identical (as for log-polar)."""
+    frame = O.lcg_frame(W, H, 77)
+    frame[..., 3] = 0x5A  # the whole 4-byte pixel is copied
+    src = dev.m.upload(frame)
+    out = dev.m.Buffer(tw * th * 4)
+    proj = fov.Projections(dev.m)
+    worst = 0.0
+    for cx, cy in [(0.5, 0.5), (0.1, 0.9), (0.0, 0.0), (1.0, 1.0), (0.73, 0.31), (0.98, 0.5)]:
+        dev.m.memset(out, 0, tw * th * 4)
+        proj.GnomonicProjection(out, tw, th, tw * 4, src, W, H, W * 4, cx, cy)
+        got = dev.m.copy_to_host(np.empty((th, tw, 4), np.uint8), out)
+        want = oracle.gnomonic(frame, tw, th, cx, cy)
+        worst = max(worst, _gather_mismatch(got, want, frame) / float(tw * th))
+    assert worst <= 1e-3, worst
+
+
+def test_interpolate_gnomonic_equals_two_kernels(dev, fov, oracle):
+    """fov_sat_interpolate_gnomonic == fov_gnomonic(fov_sat_interpolate_rect(reduced)) on the device
+    (identical index arithmetic, identical per-pixel interpolation -> bit-exact), and within the
+    gnomonic index tolerance of the oracle composition."""
+    W, H, tw, th = 1920, 1080, 960, 540
+    ow, oh = fov.reduced_dim(W), fov.reduced_dim(H)
+    frame = O.smooth_frame(W, H, seed=3)
+    _, sat_buf = dev.sat(frame)
+    proj = fov.Projections(dev.m)
+    full_buf = dev.m.Buffer(W * H * 4)
+    v1, v2 = dev.m.Buffer(tw * th * 4), dev.m.Buffer(tw * th * 4)
+    dec = dev.dec
+    for (gx, gy), (vx, vy) in [((0.5, 0.5), (0.5, 0.5)), ((0.65, 0.75), (0.6, 0.7)),
+                               ((0.02, 0.3), (0.98, 0.4)), ((0.9, 0.1), (0.2, 0.95))]:
+        red, red_buf = dev.sample(sat_buf, W, H, ow, oh, gx, gy, prefill=0x33)
+        dec.InterpolateFrameRectGPU(full_buf, W, H, W * 4, red_buf, ow, oh, ow * 4, gx, gy)
+        proj.GnomonicProjection(v1, tw, th, tw * 4, full_buf, W, H, W * 4, vx, vy)
+        proj.InterpolateGnomonicGPU(v2, tw, th, red_buf, ow, oh, W, H, gx, gy, vx, vy)
+        a = dev.m.copy_to_host(np.empty((th, tw, 4), np.uint8), v1)
+        b = dev.m.copy_to_host(np.empty((th, tw, 4), np.uint8), v2)
+        assert np.array_equal(a, b), ((gx, gy), (vx, vy))
+        want = oracle.gnomonic(oracle.sat_interpolate_rect(red, W, H, gx, gy), tw, th, vx, vy)
+        assert _gather_mismatch(b, want, None) <= 1e-3 * tw * th
+
+
 # --------------------------------------------------------------------------- ImageSampler ----
 @pytest.mark.parametrize("W,H,ow,oh", [(1920, 1080, 1072, 608), (640, 360, 368, 208)])
 def test_image_sampler_vs_oracle(dev, oracle, W, H, ow, oh):

@@ -102,6 +102,36 @@ def test_port_matches_reference_library_bit_for_bit():
                                   ref.img_interpolate_logpolar(lb, W, H, cx, cy))
 
 
+def test_gnomonic_golden_vectors(oracle):
+    """Projections::GnomonicProjection restatement against viewports rendered by the reference's
+    own kernel (tests/golden/make_golden.py: complete arrays of a small frame, hashes at 1080p)."""
+    import json
+    import os
+    gdir = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    small = dict(np.load(os.path.join(gdir, "gnomonic_small.npz")))
+    frame = small["frame"]
+    for k, (cx, cy) in enumerate(small["views"]):
+        want = small["view_%d" % k]
+        th, tw, _ = want.shape
+        assert np.array_equal(oracle.gnomonic(frame, tw, th, float(cx), float(cy)), want), k
+    with open(os.path.join(gdir, "gnomonic.json")) as fh:
+        gold = json.load(fh)
+    big = O.lcg_frame(gold["W"], gold["H"], gold["seed"])
+    for v in gold["views"]:
+        got = oracle.gnomonic(big, gold["tw"], gold["th"], v["cx"], v["cy"])
+        assert O.fnv1a64(got) == v["hash"], v
+
+
+@pytest.mark.skipif(not O.ref_available(), reason="reference library not built / not present")
+def test_gnomonic_port_matches_reference_library():
+    port, ref = O.Oracle("port"), O.Oracle("ref")
+    frame = O.lcg_frame(400, 232, 5)
+    for tw, th in [(256, 144), (333, 211), (8, 8)]:  # even sizes hit the rho == 0 centre pixel
+        for cx, cy in GAZES + [(0.73, 0.31)]:
+            assert np.array_equal(port.gnomonic(frame, tw, th, cx, cy),
+                                  ref.gnomonic(frame, tw, th, cx, cy)), (tw, th, cx, cy)
+
+
 def test_rgb24_source_stride(oracle):
     """bytes_per_pixel = linesize / width (sat_encoder_encode_kernels.cl:9): 3-byte pixels."""
     W, H = 50, 20
