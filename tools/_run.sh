@@ -1,1 +1,2 @@
-timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -8
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -4
+timeout 300 python tools/gnomonic_stats.py
