@@ -416,11 +416,12 @@ def run_e2e(args, fov, device, W, H, ow, oh, frames, gaze, dist, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="8k", choices=sorted(WORKLOADS))
-    ap.add_argument("--batch", type=int, default=8, help="frames per step per GPU")
+    ap.add_argument("--batch", type=int, default=16,
+                    help="frames per step per GPU (SURVEY 8(d): cfg3 is a batch of 16 frames)")
     ap.add_argument("--e2e-depth", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

@@ -448,7 +448,7 @@ SatOnePassPlan sat_onepass_plan(int n, int W, int H) {
   if (force_nw >= 1 && force_nw <= kMaxWarps) best = force_nw;
   p.NW = best;
   p.nsc = (p.ns + p.NW - 1) / p.NW;
-  static const int band = env_int("FOV360_SAT_BAND_ROWS", 32);
+  static const int band = env_int("FOV360_SAT_BAND_ROWS", 24);
   p.R = band < 1 ? 1 : (band > kMaxBandRows ? kMaxBandRows : band);
   p.nb = (H + p.R - 1) / p.R;
   const size_t tiles = (size_t)n * p.nb * p.nsc;
