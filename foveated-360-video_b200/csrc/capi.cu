@@ -170,6 +170,9 @@ int get_lp_grid(fov_ctx *ctx, int ow, int oh, const LogpolarGrid **out) {
     FOV_CUDA(ctx, upload(ctx, &g.d_radius, g.h_radius), "logpolar grid upload");
     FOV_CUDA(ctx, upload(ctx, &g.d_cos, g.h_cos), "logpolar grid upload");
     FOV_CUDA(ctx, upload(ctx, &g.d_sin, g.h_sin), "logpolar grid upload");
+    std::vector<double2> dir;
+    build_logpolar_directions(oh, dir);
+    FOV_CUDA(ctx, upload(ctx, &g.d_dir, dir), "logpolar grid upload");
     it = ctx->lp_grids.emplace(key, std::move(g)).first;
   }
   *out = &it->second;
@@ -248,6 +251,7 @@ void fov_ctx_destroy(fov_ctx *ctx) {
     cudaFree(kv.second.d_radius);
     cudaFree(kv.second.d_cos);
     cudaFree(kv.second.d_sin);
+    cudaFree(kv.second.d_dir);
   }
   if (ctx->sat_scratch.base) cudaFree(ctx->sat_scratch.base);
   ctx->prof.release();
@@ -710,7 +714,12 @@ int fov_img_interpolate_logpolar(fov_ctx *ctx, uint8_t *out, int W, int H, int o
       ((uintptr_t)red % 4) != 0)
     return fail(ctx, FOV_ERR_INVALID, "fov_img_interpolate_logpolar: invalid arguments");
   DeviceGuard g(ctx);
-  FOV_CUDA(ctx, launch_img_interpolate_logpolar(ctx->lc(), out, W, H, red, ow, oh, cx, cy),
+  const LogpolarGrid *grid = nullptr;  // radius / direction tables of the exact-hit check
+  int rc = get_lp_grid(ctx, ow, oh, &grid);
+  if (rc) return rc;
+  FOV_CUDA(ctx,
+           launch_img_interpolate_logpolar(ctx->lc(), out, W, H, red, ow, oh, cx, cy,
+                                           grid->d_radius, grid->d_dir),
            "img interpolate_logpolar launch");
   return FOV_OK;
 }

@@ -55,6 +55,7 @@ struct LogpolarGrid {  // ImageSampler log-polar grid, separable factors
   float *d_radius = nullptr;  // [ow]
   float *d_cos = nullptr;     // [oh]
   float *d_sin = nullptr;     // [oh]
+  double2 *d_dir = nullptr;   // [oh] (cos, sin) of the inverse warp's double-typed angle
   std::vector<float> h_radius, h_cos, h_sin;
 };
 
@@ -66,6 +67,7 @@ void build_img_grid_axes(int ow, int oh, int W, int H, std::vector<int16_t> &xd,
                          std::vector<int16_t> &yd);
 void build_logpolar_axes(int ow, int oh, std::vector<float> &radius, std::vector<float> &cs,
                          std::vector<float> &sn);
+void build_logpolar_directions(int oh, std::vector<double2> &dir);
 
 // ---- launch context: stream + optional per-kernel event timing ------------------------------
 
@@ -173,7 +175,7 @@ cudaError_t launch_img_sample_logpolar(const LaunchCtx &lc, uint8_t *out, int ow
                                        const float *sn, float cx, float cy);
 cudaError_t launch_img_interpolate_logpolar(const LaunchCtx &lc, uint8_t *out, int W, int H,
                                             const uint8_t *red, int ow, int oh, float cx,
-                                            float cy);
+                                            float cy, const float *radius, const double2 *dir);
 cudaError_t launch_img_logpolar_blur(const LaunchCtx &lc, uint8_t *out, int ow, int oh,
                                      const uint8_t *src);
 cudaError_t launch_img_logpolar_grid_expand(const LaunchCtx &lc, int16_t *grid, int ow, int oh,

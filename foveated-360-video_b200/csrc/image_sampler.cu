@@ -107,13 +107,15 @@ __device__ __forceinline__ uint32_t lerp_pixel(uint32_t tl, uint32_t tr, uint32_
   return outp;
 }
 
-// interpolate_logpolar_kernel (image_sampler_interpolate_kernel.cl:1-81).  Not separable, so
-// the transcendentals are evaluated per pixel.  Where the reference's typing promotes to
-// double the same is done here; single-precision libm calls are evaluated in double and
-// rounded once, which reproduces a (nearly always) correctly rounded host libm result.
+// interpolate_logpolar_kernel (image_sampler_interpolate_kernel.cl:1-81).  Not separable: the
+// radius logarithm and the angle arctangent are evaluated per pixel (where the reference's typing
+// promotes to double the same is done here; single-precision libm calls are evaluated in double
+// and rounded once, which reproduces a - nearly always - correctly rounded host libm result).
+// The forward map of the exact-hit check (:46-51) only depends on the rounded indices, so its
+// exp / cos / sin come from the host-built radius[ow] and direction[oh] tables.
 __global__ void __launch_bounds__(256) img_interpolate_logpolar_kernel(
     uint32_t *__restrict__ out, int W, int H, const uint32_t *__restrict__ red, int ow, int oh,
-    float cx, float cy) {
+    float cx, float cy, const float *__restrict__ radius, const double2 *__restrict__ dir) {
   const int xx = blockIdx.x * 32 + threadIdx.x;
   const int yy = blockIdx.y * 8 + threadIdx.y;
   if (xx >= W || yy >= H) return;
@@ -138,15 +140,20 @@ __global__ void __launch_bounds__(256) img_interpolate_logpolar_kernel(
     const float q = __fdiv_rn((float)dy, (float)dx);
     const float at = (float)atan((double)q);
     j_f = (float)(((double)at + kPi * (double)(dx < 0)) * ((double)(float)oh / (2.0 * kPi)));
-    j_f = (float)fmod((double)__fadd_rn(j_f, (float)(2 * oh)), (double)oh);
+    // fmod(j_f + 2 oh, oh), :39: the argument is a float in (1.75 oh, 2.75 oh), so the remainder is
+    // one or two subtractions of oh, each exact in double (24-bit operand, oh < 2^15)
+    double wrapped = (double)__fadd_rn(j_f, (float)(2 * oh));
+    const double period = (double)oh;
+    while (wrapped >= period) wrapped -= period;
+    j_f = (float)wrapped;
   } else {  // :41-43
     j_f = (float)((kPi2 + kPi * (double)(dy < 0)) * ((double)oh / (2.0 * kPi)));
   }
   const int j = clampi((int)roundf(j_f), 0, oh - 1);  // :44
-  const float rad = (float)exp((double)__fmul_rn(10.0f, __fdiv_rn((float)i, (float)ow)));
-  const double ang = (double)__fmul_rn(__fdiv_rn((float)j, (float)oh), 2.0f) * kPi;
-  const int calc_x = __double2int_rz((double)__fmul_rn(cx, (float)W) + (double)rad * cos(ang));
-  const int calc_y = __double2int_rz((double)__fmul_rn(cy, (float)H) + (double)rad * sin(ang));
+  const float rad = __ldg(radius + i);  // expf(10.0f * powf((float)i / ow, alpha)), :47
+  const double2 cs = __ldg(dir + j);    // cos, sin of (float)j / oh * 2.0f * M_PI
+  const int calc_x = __double2int_rz(__dadd_rn((double)__fmul_rn(cx, (float)W), __dmul_rn((double)rad, cs.x)));
+  const int calc_y = __double2int_rz(__dadd_rn((double)__fmul_rn(cy, (float)H), __dmul_rn((double)rad, cs.y)));
   uint32_t v;
   if (calc_x == x && calc_y == y) {  // :53-55
     v = __ldg(red + (size_t)j * ow + i);
@@ -241,12 +248,12 @@ cudaError_t launch_img_sample_logpolar(const LaunchCtx &lc, uint8_t *out, int ow
 
 cudaError_t launch_img_interpolate_logpolar(const LaunchCtx &lc, uint8_t *out, int W, int H,
                                             const uint8_t *red, int ow, int oh, float cx,
-                                            float cy) {
+                                            float cy, const float *radius, const double2 *dir) {
   const dim3 grid((W + 31) / 32, (H + 7) / 8), block(32, 8);
   KernelScope ks(lc, "img_interpolate_logpolar");
   img_interpolate_logpolar_kernel<<<grid, block, 0, lc.stream>>>(
       reinterpret_cast<uint32_t *>(out), W, H, reinterpret_cast<const uint32_t *>(red), ow, oh, cx,
-      cy);
+      cy, radius, dir);
   return cudaGetLastError();
 }
 

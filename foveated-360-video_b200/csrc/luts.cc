@@ -122,6 +122,17 @@ void build_logpolar_axes(int ow, int oh, std::vector<float> &radius, std::vector
   }
 }
 
+// Direction table of the log-polar inverse warp (image_sampler_interpolate_kernel.cl:46-51):
+// cos / sin of (float)j / oh * 2.0f * M_PI - the float product is promoted by the double M_PI.
+void build_logpolar_directions(int oh, std::vector<double2> &dir) {
+  dir.resize(oh);
+  for (int j = 0; j < oh; ++j) {
+    const double a = (double)((float)j / oh * 2.0f) * 3.14159265358979323846;
+    dir[j].x = cos(a);
+    dir[j].y = sin(a);
+  }
+}
+
 // Gnomonic viewport constants (projections_program.cl:25-28): (center - 0.5) is promoted to
 // double by the double literals 0.5 / PI and narrowed to float on assignment; sin/cos of the float.
 GnomonicView make_gnomonic_view(float cx, float cy) {
