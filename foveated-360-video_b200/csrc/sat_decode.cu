@@ -403,9 +403,12 @@ __global__ void __launch_bounds__(32 * kInterpWarps, FOV360_INTERP_MIN_CTAS)
   const uint32_t *red = reinterpret_cast<const uint32_t *>(a.red + (size_t)f * a.red_stride);
 
   // ---- x axis: once per lane ------------------------------------------------------------
+  // mix(l, r, 0) returns l exactly, so a zero ratio needs one tap.  mix(l, r, 1) = l + (r - l) is
+  // r only when l and r are integer-valued (copy rows); after a vertical mix it can round one ulp
+  // away from r, so ratio-one pixels keep both taps.
   int xlo[kInterpPx], xhi[kInterpPx], xex[kInterpPx];
   float xr[kInterpPx];
-  bool all_deg = true, simple = true;
+  bool unit_x = true, simple = true, need_left = false;
   int cmin = 0x7fffffff, cmax = -1;
 #pragma unroll
   for (int k = 0; k < kInterpPx; ++k) {
@@ -420,18 +423,25 @@ __global__ void __launch_bounds__(32 * kInterpWarps, FOV360_INTERP_MIN_CTAS)
     }
     const int dx = clampi(x - cxp, -W, W);
     const AxisSel sx = resolve_axis(load_entry(a.lx + (dx + W)), cxp, W, ow, wrapped);
-    const bool deg = sx.ratio == 0.0f || sx.ratio == 1.0f;
-    const int sel = sx.ratio == 1.0f ? sx.hi : sx.lo;
-    xlo[k] = deg ? sel : sx.lo;  // degenerate: both taps are the selected column
-    xhi[k] = deg ? sel : sx.hi;
+    const bool zero = sx.ratio == 0.0f, one = sx.ratio == 1.0f;
+    xlo[k] = sx.lo;
+    xhi[k] = zero ? sx.lo : sx.hi;
     xr[k] = sx.ratio;
     xex[k] = sx.exact ? sx.exact_idx : -1;
-    all_deg = all_deg && deg;
-    simple = simple && (xex[k] < 0 || (xex[k] == xlo[k] && xhi[k] == xlo[k]));
+    // 1:1 path: every pixel is its primary column (hi for ratio one, lo for ratio zero), and the
+    // left tap of a ratio-one pixel is the primary column of the pixel before it
+    unit_x = unit_x && (zero || one);
+    if (one && xhi[k] != xlo[k]) {
+      need_left = true;
+      if (k > 0) unit_x = unit_x && xlo[k] == (xr[k - 1] == 1.0f ? xhi[k - 1] : xlo[k - 1]);
+    }
+    // fast paths: an exact hit must be the primary tap
+    simple = simple && (xex[k] < 0 || (zero && xex[k] == xlo[k]) || (one && xex[k] == xhi[k]));
     cmin = min(cmin, min(xlo[k], xhi[k]));
     cmax = max(cmax, max(xlo[k], xhi[k]));
   }
-  all_deg = __all_sync(0xffffffffu, all_deg);
+  unit_x = __all_sync(0xffffffffu, unit_x);
+  need_left = __any_sync(0xffffffffu, need_left);
   cmin = __reduce_min_sync(0xffffffffu, cmin);
   cmax = __reduce_max_sync(0xffffffffu, cmax);
   const int ncols = cmax - cmin + 1;
@@ -465,6 +475,9 @@ __global__ void __launch_bounds__(32 * kInterpWarps, FOV360_INTERP_MIN_CTAS)
   const int nrows = min(kInterpRows, H - y0);
   // the fast paths below also assume one aligned 16-byte store per lane and row
   simple = __all_sync(0xffffffffu, simple && vec_ok);  // (orders the rowsel writes, too)
+#ifdef FOV360_INTERP_FORCE_GENERIC
+  simple = false;
+#endif
 
   auto store_row = [&](const uint32_t (&px)[kInterpPx]) {
     if (vec_ok) {
@@ -476,21 +489,27 @@ __global__ void __launch_bounds__(32 * kInterpWarps, FOV360_INTERP_MIN_CTAS)
     }
   };
 
-  if (simple && all_deg) {
-    // ---- every pixel maps onto a single reduced column: vertical mix (or copy) only ----------
+  if (simple && unit_x) {
+    // ---- every pixel sits on its primary reduced column: vertical mix (or copy) only, plus for
+    // ratio-one pixels the rounding of l + (r - l) with l = the column to the left ---------------
     const uint32_t *col[kInterpPx];
     uint32_t keep[kInterpPx];  // bytes an exact-hit row copies: all 4 where x is an exact hit too
+    bool one[kInterpPx];
 #pragma unroll
     for (int k = 0; k < kInterpPx; ++k) {
-      col[k] = red + xlo[k];
+      one[k] = xr[k] == 1.0f && xhi[k] != xlo[k];
+      col[k] = red + (xr[k] == 1.0f ? xhi[k] : xlo[k]);
       keep[k] = xex[k] >= 0 ? 0xffffffffu : 0x00ffffffu;
     }
-    TapPair tp[kInterpPx] = {};
+    const uint32_t *col_left = red + xlo[0];  // left tap of pixel 0 (when it is a ratio-one pixel)
+    const bool all_one = __all_sync(0xffffffffu, one[0] && one[1] && one[2] && one[3]);
+    TapPair tp[kInterpPx] = {}, tpl = {};
     int r = 0;
     while (r < nrows) {
       const RowSel rs = rowsel[warp][r];
       if (rs.off_lo == rs.off_hi) {
-        // Copy rows (1:1 on both axes) come in long runs: four rows of loads in flight per batch.
+        // Copy rows (integer-valued taps: l + (r - l) == r) come in long runs: four rows of loads
+        // in flight per batch.
         int nb = 1;
         RowSel b[4];
         b[0] = rs;
@@ -522,13 +541,47 @@ __global__ void __launch_bounds__(32 * kInterpWarps, FOV360_INTERP_MIN_CTAS)
 #pragma unroll
           for (int k = 0; k < kInterpPx; ++k)
             convert_tap_pair(tp[k], __ldg(col[k] + rs.off_lo), __ldg(col[k] + rs.off_hi));
+          if (need_left) convert_tap_pair(tpl, __ldg(col_left + rs.off_lo), __ldg(col_left + rs.off_hi));
         }
-        uint32_t px[kInterpPx];
+        float v[kInterpPx][3];
 #pragma unroll
         for (int k = 0; k < kInterpPx; ++k)
-          px[k] = pack_rgb0(trunc_bits(lerp_rn(tp[k].p[0], tp[k].d[0], rs.ty)),
-                            trunc_bits(lerp_rn(tp[k].p[1], tp[k].d[1], rs.ty)),
-                            trunc_bits(lerp_rn(tp[k].p[2], tp[k].d[2], rs.ty)));
+#pragma unroll
+          for (int c = 0; c < 3; ++c) v[k][c] = lerp_rn(tp[k].p[c], tp[k].d[c], rs.ty);
+        uint32_t px[kInterpPx];
+        if (all_one) {  // warp-uniform: right of the gaze every pixel is mix(l, r, 1) = l + (r - l)
+          float l[3];
+#pragma unroll
+          for (int c = 0; c < 3; ++c) l[c] = lerp_rn(tpl.p[c], tpl.d[c], rs.ty);
+#pragma unroll
+          for (int k = 0; k < kInterpPx; ++k) {
+            float o[3];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+              o[c] = __fadd_rn(l[c], __fsub_rn(v[k][c], l[c]));  // (r - l) * 1.0f is exact
+              l[c] = v[k][c];
+            }
+            px[k] = pack_rgb0(trunc_bits(o[0]), trunc_bits(o[1]), trunc_bits(o[2]));
+          }
+        } else if (need_left) {  // warp-uniform: the warp that holds the gaze column
+          float l[3];
+#pragma unroll
+          for (int c = 0; c < 3; ++c) l[c] = lerp_rn(tpl.p[c], tpl.d[c], rs.ty);
+#pragma unroll
+          for (int k = 0; k < kInterpPx; ++k) {
+            float o[3];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+              o[c] = one[k] ? __fadd_rn(l[c], __fsub_rn(v[k][c], l[c])) : v[k][c];
+              l[c] = v[k][c];
+            }
+            px[k] = pack_rgb0(trunc_bits(o[0]), trunc_bits(o[1]), trunc_bits(o[2]));
+          }
+        } else {
+#pragma unroll
+          for (int k = 0; k < kInterpPx; ++k)
+            px[k] = pack_rgb0(trunc_bits(v[k][0]), trunc_bits(v[k][1]), trunc_bits(v[k][2]));
+        }
         store_row(px);
         orow += W;
         ++r;
@@ -541,12 +594,13 @@ __global__ void __launch_bounds__(32 * kInterpWarps, FOV360_INTERP_MIN_CTAS)
   if (simple && ncols <= 32) {
     // ---- periphery: lane c owns window column c ---------------------------------------------
     const float4 *pv[kInterpPx];
-    uint32_t keep[kInterpPx];
+    uint32_t keep_lo[kInterpPx], keep_hi[kInterpPx];  // 4th byte of an exact hit: from V.w or D.w
 #pragma unroll
     for (int k = 0; k < kInterpPx; ++k) {
       pv[k] = vs + (xlo[k] - cmin);
+      keep_lo[k] = (xex[k] >= 0 && xex[k] == xlo[k]) ? 0xff000000u : 0u;
+      keep_hi[k] = (xex[k] >= 0 && xex[k] != xlo[k]) ? 0xff000000u : 0u;
       if (xhi[k] == xlo[k]) xr[k] = 0.0f;  // V + D * 0 = V: the selected column, exactly
-      keep[k] = xex[k] >= 0 ? 0xff000000u : 0u;
     }
     // lanes past the window repeat its last column: every V and D stays finite, and the D of the
     // last column (0, or never multiplied by a non-zero tx) needs no special case
@@ -569,10 +623,12 @@ __global__ void __launch_bounds__(32 * kInterpWarps, FOV360_INTERP_MIN_CTAS)
       const float n0 = __shfl_down_sync(0xffffffffu, v0, 1);
       const float n1 = __shfl_down_sync(0xffffffffu, v1, 1);
       const float n2 = __shfl_down_sync(0xffffffffu, v2, 1);
-      const uint32_t alpha = rs.info >= 0 ? (rawp[j] & 0xff000000u) : 0u;  // exact-hit rows
+      // exact-hit rows: V.w carries the sample's 4th byte, D.w that of the column to the right
+      const uint32_t alpha = rs.info >= 0 ? (rawp[j] & 0xff000000u) : 0u;
+      const uint32_t alpha_next = __shfl_down_sync(0xffffffffu, alpha, 1);
       vs[j * 32 + lane] = make_float4(v0, v1, v2, __uint_as_float(alpha));
-      vs[(kInterpChunk + j) * 32 + lane] =
-          make_float4(__fsub_rn(n0, v0), __fsub_rn(n1, v1), __fsub_rn(n2, v2), 0.f);
+      vs[(kInterpChunk + j) * 32 + lane] = make_float4(
+          __fsub_rn(n0, v0), __fsub_rn(n1, v1), __fsub_rn(n2, v2), __uint_as_float(alpha_next));
     };
     request(0);
     for (int r0 = 0; r0 < nrows; r0 += kInterpChunk) {
@@ -605,7 +661,8 @@ __global__ void __launch_bounds__(32 * kInterpWarps, FOV360_INTERP_MIN_CTAS)
 #pragma unroll
         for (int k = 0; k < kInterpPx; ++k) {
           const float4 v = pv[k][j * 32], d = pv[k][(kInterpChunk + j) * 32];
-          px[k] = lerp_px(v, d, xr[k]) | (__float_as_uint(v.w) & keep[k]);
+          px[k] = lerp_px(v, d, xr[k]) | (__float_as_uint(v.w) & keep_lo[k]) |
+                  (__float_as_uint(d.w) & keep_hi[k]);
         }
         if (r0 + j < nrows) __stcs(orow4, make_uint4(px[0], px[1], px[2], px[3]));
         orow4 += W / 4;
@@ -721,11 +778,7 @@ __global__ void __launch_bounds__(256) sat_interpolate_gnomonic_kernel(
   if (sx.exact && sy.exact) {  // :67-72: all 4 bytes of the sample
     px = __ldg(red + (size_t)sy.exact_idx * ow + sx.exact_idx);
   } else {
-    // a ratio of exactly 0 or 1 selects one tap (mix() returns that operand unchanged)
-    const bool xdeg = sx.ratio == 0.0f || sx.ratio == 1.0f, ydeg = sy.ratio == 0.0f || sy.ratio == 1.0f;
-    const int xsel = sx.ratio == 1.0f ? sx.hi : sx.lo, ysel = sy.ratio == 1.0f ? sy.hi : sy.lo;
-    const int xlo = xdeg ? xsel : sx.lo, xhi = xdeg ? xsel : sx.hi;
-    const int ylo = ydeg ? ysel : sy.lo, yhi = ydeg ? ysel : sy.hi;
+    const int xlo = sx.lo, xhi = sx.hi, ylo = sy.lo, yhi = sy.hi;
     const uint32_t *ra = red + (size_t)ylo * ow, *rb = red + (size_t)yhi * ow;
     const uint32_t tl = __ldg(ra + xlo), tr = __ldg(ra + xhi);
     const uint32_t bl = __ldg(rb + xlo), br = __ldg(rb + xhi);

@@ -209,6 +209,44 @@ def test_sample_and_interpolate_vs_oracle(dev, oracle, W, H, ow, oh):
         assert worst <= 1, (cx, cy, int((full != wfull).sum()))
 
 
+@pytest.mark.parametrize("W,H", [(1000, 500), (1002, 501), (132, 70), (2052, 24), (516, 1031)])
+def test_ragged_geometries_full_pipeline(dev, fov, oracle, W, H):
+    """Sizes that leave partial tiles everywhere: widths that are not multiples of 128 (partial SAT
+    strips, partial interpolate warps) or of 4 (generic SAT path, scalar stores), heights that are
+    not multiples of the band / warp-tile heights, single-band and single-strip frames; single calls
+    and one fused batched call (source-hint path) against the oracle, everything bit-exact."""
+    ow, oh = fov.reduced_dim(W), fov.reduced_dim(H)
+    frames = np.stack([O.lcg_frame(W, H, 100 + f) for f in range(3)])
+    frames[..., 3] = 0x7F
+    gaze = np.array([[0.5, 0.5], [0.03, 0.96], [0.97, 0.08]], np.float32)
+    want_sat = [oracle.sat_encode(f) for f in frames]
+    sat, sat_buf = dev.sat(frames[0])
+    assert np.array_equal(sat, want_sat[0])
+    for cx, cy in [(0.5, 0.5), (0.0, 1.0), (0.31, 0.77)]:
+        red, _ = dev.sample(sat_buf, W, H, ow, oh, cx, cy)
+        want = oracle.sat_sample_rect(sat, ow, oh, cx, cy, out=ab(oh, ow))
+        assert np.array_equal(red, want), (cx, cy)
+        full = dev.interpolate(want, W, H, cx, cy)
+        assert np.array_equal(full, oracle.sat_interpolate_rect(want, W, H, cx, cy)), (cx, cy)
+    n = len(frames)
+    src = dev.m.upload(frames)
+    sats = dev.m.Buffer(n * W * H * 12)
+    red = dev.m.upload(np.full((n, oh, ow, 4), 0xAB, np.uint8))
+    full = dev.m.Buffer(n * W * H * 4)
+    fov.FoveateFramesGPU(dev.m, n, full, W * H * 4, red, ow * oh * 4, sats, W * H * 12, src,
+                         W * H * 4, W, H, 4 * W, ow, oh, gaze)
+    got_sat = dev.m.copy_to_host(np.empty((n, H, W, 3), np.uint32), sats)
+    got_red = dev.m.copy_to_host(np.empty((n, oh, ow, 4), np.uint8), red)
+    got_full = dev.m.copy_to_host(np.empty((n, H, W, 4), np.uint8), full)
+    for f in range(n):
+        assert np.array_equal(got_sat[f], want_sat[f]), f
+        r = oracle.sat_sample_rect(want_sat[f], ow, oh, float(gaze[f, 0]), float(gaze[f, 1]),
+                                   out=ab(oh, ow))
+        assert np.array_equal(got_red[f], r), f
+        w = oracle.sat_interpolate_rect(r, W, H, float(gaze[f, 0]), float(gaze[f, 1]))
+        assert np.array_equal(got_full[f], w), f
+
+
 def test_sample_padded_target_linesize(dev, oracle):
     W, H, ow, oh = 640, 360, 368, 208
     frame = O.lcg_frame(W, H, 4)

@@ -1,2 +1,2 @@
-timeout 900 python -m pytest tests -m gpu -x -q -k "image_sampler or golden or dropin" 2>&1 | tail -3
-timeout 200 python tools/logpolar_bench.py --workload 4k 2>/dev/null | head -1
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
+timeout 120 python tools/stage_bench.py --batch 16 --tag exact2
