@@ -24,6 +24,12 @@ def max_lsb(a, b):
     return int(np.abs(a.astype(np.int16) - b.astype(np.int16)).max())
 
 
+# interpolate_rect's contract with the reference is <= 1 LSB (FMA contraction of mix()
+# on a real OpenCL device); against the oracle's un-fused float arithmetic this implementation is
+# bit-exact, and the tests hold it to that.
+INTERP_TOL = 0
+
+
 class Dev:
     """Call-sequence helper written like the reference's call sites (video_server.cc:296-345)."""
 
@@ -76,7 +82,7 @@ def test_small_golden_vectors(dev, small):
         red, _ = dev.sample(sat_buf, W, H, ow, oh, cx, cy)
         assert np.array_equal(red, small["reduced_%d" % k]), k
         full = dev.interpolate(small["reduced_%d" % k], W, H, cx, cy)
-        assert max_lsb(full[..., :3], small["interp_%d" % k][..., :3]) <= 1
+        assert max_lsb(full[..., :3], small["interp_%d" % k][..., :3]) <= INTERP_TOL
         out = dev.m.upload(ab(oh, ow))
         dev.img.SampleFrameLogPolarGPU(out, ow, oh, 4 * ow, src, W, H, 4 * W, cx, cy)
         lp = dev.m.copy_to_host(ab(oh, ow), out)
@@ -113,7 +119,7 @@ def test_golden_hashes_sat_path(dev, golden, idx):
         full = dev.interpolate(red, W, H, g["cx"], g["cy"])
         if O.fnv1a64(full) != g["interp"]:  # tolerance path: <= 1 LSB vs the oracle
             want = O.port().sat_interpolate_rect(red, W, H, g["cx"], g["cy"])
-            assert max_lsb(full[..., :3], want[..., :3]) <= 1
+            assert max_lsb(full[..., :3], want[..., :3]) <= INTERP_TOL
 
 
 def test_golden_grid_hashes(dev, golden):
@@ -206,7 +212,7 @@ def test_sample_and_interpolate_vs_oracle(dev, oracle, W, H, ow, oh):
         full = dev.interpolate(want, W, H, cx, cy)
         wfull = oracle.sat_interpolate_rect(want, W, H, cx, cy)
         worst = max(worst, max_lsb(full[..., :3], wfull[..., :3]))
-        assert worst <= 1, (cx, cy, int((full != wfull).sum()))
+        assert worst <= INTERP_TOL, (cx, cy, int((full != wfull).sum()))
 
 
 @pytest.mark.parametrize("W,H", [(1000, 500), (1002, 501), (132, 70), (2052, 24), (516, 1031)])
@@ -270,7 +276,8 @@ def test_gaze_sweep_9x9_4k(dev, oracle):
         assert np.array_equal(red, want), (cx, cy)
         if k % 10 == 0:
             full = dev.interpolate(want, W, H, cx, cy)
-            assert max_lsb(full[..., :3], oracle.sat_interpolate_rect(want, W, H, cx, cy)[..., :3]) <= 1
+            assert max_lsb(full[..., :3],
+                           oracle.sat_interpolate_rect(want, W, H, cx, cy)[..., :3]) <= INTERP_TOL
 
 
 def test_roundtrip_identity_near_gaze_8k(dev):
@@ -308,7 +315,7 @@ def test_batched_pipeline_matches_single_calls(dev, fov, oracle):
         r = oracle.sat_sample_rect(s, ow, oh, float(gaze[f, 0]), float(gaze[f, 1]))
         assert np.array_equal(got_red[f], r), f
         w = oracle.sat_interpolate_rect(r, W, H, float(gaze[f, 0]), float(gaze[f, 1]))
-        assert max_lsb(got_full[f][..., :3], w[..., :3]) <= 1, f
+        assert max_lsb(got_full[f][..., :3], w[..., :3]) <= INTERP_TOL, f
 
 
 def test_fused_pipeline_unit_boxes_read_source(dev, fov, oracle):
@@ -335,7 +342,7 @@ def test_fused_pipeline_unit_boxes_read_source(dev, fov, oracle):
                                    out=prefill[f].copy())
         assert np.array_equal(got_red[f], r), f
         w = oracle.sat_interpolate_rect(r, W, H, float(gaze[f, 0]), float(gaze[f, 1]))
-        assert max_lsb(got_full[f], w) <= 1, f
+        assert max_lsb(got_full[f], w) <= INTERP_TOL, f
 
 
 # ---------------------------------------------------------------------------- Projections ----
