@@ -392,28 +392,22 @@ __global__ void __launch_bounds__(32 * kInterpWarps, FOV360_INTERP_MIN_CTAS)
       2 * (kInterpChunk * 32 > kInterpMaxCols ? kInterpChunk * 32 : kInterpMaxCols);
   __shared__ float4 vstage[kInterpWarps][kStage];  // V and D of the column window
   __shared__ RowSel rowsel[kInterpWarps][kInterpRows];
+  __shared__ int4 xsel[kInterpPx][32];
   const int lane = threadIdx.x, warp = threadIdx.y;
   const int x4 = (blockIdx.x * 32 + lane) * kInterpPx;
   const int y0 = (blockIdx.y * kInterpWarps + warp) * kInterpRows;
   const int f = blockIdx.z;
-  if (y0 >= a.H) return;  // warp-uniform
   const int W = a.W, H = a.H, ow = a.ow, oh = a.oh;
   const int cxp = gaze_px(g.xy[2 * f], W);
   const int cyp = gaze_px(g.xy[2 * f + 1], H);
   const uint32_t *red = reinterpret_cast<const uint32_t *>(a.red + (size_t)f * a.red_stride);
 
-  // ---- x axis: once per lane ------------------------------------------------------------
-  // mix(l, r, 0) returns l exactly, so a zero ratio needs one tap.  mix(l, r, 1) = l + (r - l) is
-  // r only when l and r are integer-valued (copy rows); after a vertical mix it can round one ulp
-  // away from r, so ratio-one pixels keep both taps.
-  int xlo[kInterpPx], xhi[kInterpPx], xex[kInterpPx];
-  float xr[kInterpPx];
-  bool unit_x = true, simple = true, need_left = false;
-  int cmin = 0x7fffffff, cmax = -1;
-#pragma unroll
-  for (int k = 0; k < kInterpPx; ++k) {
-    int x = min(x4 + k, W - 1);  // lanes past the right edge repeat the last pixel (never stored)
-    bool wrapped = false;        // :26-33
+  // ---- x axis: resolved once per CTA (its warps cover the same 128 columns): warp k resolves
+  // pixel k of every lane --------------------------------------------------------------------
+  static_assert(kInterpWarps == kInterpPx, "one warp per pixel slot");
+  {
+    int x = min(x4 + warp, W - 1);  // lanes past the right edge repeat the last pixel (never stored)
+    bool wrapped = false;           // :26-33
     if (x - cxp > W / 2) {
       x -= W;
       wrapped = true;
@@ -423,11 +417,26 @@ __global__ void __launch_bounds__(32 * kInterpWarps, FOV360_INTERP_MIN_CTAS)
     }
     const int dx = clampi(x - cxp, -W, W);
     const AxisSel sx = resolve_axis(load_entry(a.lx + (dx + W)), cxp, W, ow, wrapped);
-    const bool zero = sx.ratio == 0.0f, one = sx.ratio == 1.0f;
-    xlo[k] = sx.lo;
-    xhi[k] = zero ? sx.lo : sx.hi;
-    xr[k] = sx.ratio;
-    xex[k] = sx.exact ? sx.exact_idx : -1;
+    xsel[warp][lane] = make_int4(sx.lo, sx.hi, __float_as_int(sx.ratio), sx.exact ? sx.exact_idx : -1);
+  }
+  __syncthreads();
+  if (y0 >= H) return;  // warp-uniform
+
+  // mix(l, r, 0) returns l exactly, so a zero ratio needs one tap.  mix(l, r, 1) = l + (r - l) is
+  // r only when l and r are integer-valued (copy rows); after a vertical mix it can round one ulp
+  // away from r, so ratio-one pixels keep both taps.
+  int xlo[kInterpPx], xhi[kInterpPx], xex[kInterpPx];
+  float xr[kInterpPx];
+  bool unit_x = true, simple = true, need_left = false;
+  int cmin = 0x7fffffff, cmax = -1;
+#pragma unroll
+  for (int k = 0; k < kInterpPx; ++k) {
+    const int4 sx = xsel[k][lane];
+    xr[k] = __int_as_float(sx.z);
+    const bool zero = xr[k] == 0.0f, one = xr[k] == 1.0f;
+    xlo[k] = sx.x;
+    xhi[k] = zero ? sx.x : sx.y;
+    xex[k] = sx.w;
     // 1:1 path: every pixel is its primary column (hi for ratio one, lo for ratio zero), and the
     // left tap of a ratio-one pixel is the primary column of the pixel before it
     unit_x = unit_x && (zero || one);
