@@ -1,4 +1,3 @@
-for nw in 4 5 6; do FOV360_SAT_WARPS=$nw timeout 120 python tools/stage_bench.py --batch 16 --tag NW$nw | grep "onepass"; done
-for v in 1 3; do FOV360_SAT_VARIANT=$v FOV360_SAT_TMA_STORE=0 timeout 120 python tools/stage_bench.py --batch 16 --tag var$v | grep "onepass"; done
-FOV360_SAT_POLICY=1 timeout 120 python tools/stage_bench.py --batch 16 --tag pol1 | grep "onepass"
-FOV360_SAT_POLICY=3 timeout 120 python tools/stage_bench.py --batch 16 --tag pol3 | grep "onepass"
+for r in 16 24 32; do for nw in 5 6; do echo "R=$r NW=$nw"; FOV360_SAT_BAND_ROWS=$r FOV360_SAT_WARPS=$nw timeout 120 python tools/stage_bench.py --workload 4k --batch 8 --steps 50 | grep "onepass"; done; done
+timeout 120 python tools/stage_bench.py --workload 4k --batch 8 --steps 50
+timeout 120 python tools/stage_bench.py --workload 1080p --batch 16 --steps 50

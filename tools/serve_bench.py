@@ -1,0 +1,83 @@
+#!/usr/bin/env python3
+"""BASELINE configs[4]: concurrent 4K streams with independent per-frame gaze
+traces, stream s pinned to GPU s % G, the streams of one GPU foveated by one batched call per frame
+time.  Run under torchrun for G > 1; a single process plays rank 0 of `--world` GPUs.
+
+    python tools/serve_bench.py [--streams 64] [--world 8] [--frames 300]
+    python -m torch.distributed.run --nproc-per-node 8 tools/serve_bench.py
+"""
+import argparse
+import importlib
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import bench  # noqa: E402
+
+
+def gaze_walk(stream: int, frames: int) -> np.ndarray:
+    """Smooth random walk, sigma 0.01 per frame, reflected at 0 and 1, seeded by the stream id."""
+    rng = np.random.default_rng(stream)
+    p = rng.random(2)
+    out = np.empty((frames, 2), np.float32)
+    for t in range(frames):
+        p = p + rng.normal(0.0, 0.01, 2)
+        p = np.abs(p)
+        p = 1.0 - np.abs(1.0 - p)
+        out[t] = p
+    return out
+
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--streams", type=int, default=64)
+ap.add_argument("--world", type=int, default=8, help="GPUs the streams are spread over")
+ap.add_argument("--frames", type=int, default=300)
+ap.add_argument("--workload", default="4k")
+args = ap.parse_args()
+
+rank = int(os.environ.get("RANK", 0))
+world = int(os.environ.get("WORLD_SIZE", args.world)) if "RANK" in os.environ else args.world
+dist = None
+if "RANK" in os.environ and int(os.environ.get("WORLD_SIZE", 1)) > 1:
+    import torch.distributed as dist
+
+    dist.init_process_group("nccl" if os.environ.get("FOV_DIST", "nccl") == "nccl" else "gloo")
+fov = importlib.import_module("foveated-360-video_b200")
+mine = fov.sharding.streams_for_rank(args.streams, world, rank)
+n = len(mine)
+W, H = bench.WORKLOADS[args.workload]
+ow, oh = bench.reduced(W), bench.reduced(H)
+m = fov.OpenCLManager(int(os.environ.get("LOCAL_RANK", 0)))
+m.InitializeContext()
+fb, sb, rb = 4 * W * H, 12 * W * H, 4 * ow * oh
+base = bench.synth_frame(W, H, 0)
+frames = np.stack([np.roll(base, 131 * s, axis=1) for s in mine])
+src, sat, red, full = m.upload(frames), m.Buffer(n * sb), m.Buffer(n * rb), m.Buffer(n * fb)
+m.memset(red, 0, n * rb)
+traces = np.stack([gaze_walk(s, args.frames + 3) for s in mine], axis=1)  # [frame][stream][2]
+for t in range(3):
+    fov.FoveateFramesGPU(m, n, full, fb, red, rb, sat, sb, src, fb, W, H, 4 * W, ow, oh, traces[t])
+m.profile_reset()
+m.profile(True)
+for t in range(args.frames):
+    fov.FoveateFramesGPU(m, n, full, fb, red, rb, sat, sb, src, fb, W, H, 4 * W, ow, oh, traces[3 + t])
+tot = m.profile_totals()
+m.profile(False)
+sec = sum(v[0] for v in tot.values()) / 1e3
+sec = fov.sharding.reduce_max_seconds(sec, dist, "cuda" if dist else None)
+if rank == 0:
+    ranks = int(os.environ.get("WORLD_SIZE", 1)) if dist else 1
+    print(json.dumps({
+        "workload": "%d concurrent %s streams over %d GPU(s), stream s -> GPU s %% %d, %d frames each, "
+                    "random-walk gaze" % (args.streams, args.workload, world, world, args.frames),
+        "gpus_measured": ranks, "streams_per_gpu": n,
+        "frame_time_ms": round(sec / args.frames * 1e3, 4),
+        "fps_per_stream": round(args.frames / sec, 1),
+        "frames_per_s_measured_gpus": round(ranks * n * args.frames / sec, 1)}))
+m.close()
+if dist:
+    dist.destroy_process_group()
