@@ -196,6 +196,25 @@ def test_batched_encode_matches_single(dev, oracle):
         assert np.array_equal(got[f], oracle.sat_encode(frames[f])), f
 
 
+def test_sat_alternating_layouts_and_batches(dev, oracle):
+    """The one-pass SAT scratch (ticket counters, epoch-tagged carry units) is reused across calls:
+    alternate tile layouts and batch sizes on one context and check every result."""
+    rng = np.random.default_rng(9)
+    cases = [(512, 96, 1), (1280, 720, 3), (512, 96, 2), (260, 50, 5), (1280, 720, 1), (260, 50, 5)]
+    want = {}
+    for rnd in range(2):
+        for W, H, n in cases:
+            frames = rng.integers(0, 256, (n, H, W, 4), dtype=np.uint8)
+            src = dev.m.upload(frames)
+            sat = dev.m.Buffer(n * W * H * 12)
+            dev.enc.EncodeFramesGPU(n, sat, W * H * 12, src, W * H * 4, W, H, 4 * W)
+            got = dev.m.copy_to_host(np.empty((n, H, W, 3), np.uint32), sat)
+            for f in range(n):
+                assert np.array_equal(got[f], oracle.sat_encode(frames[f])), (rnd, W, H, n, f)
+            src.free()
+            sat.free()
+
+
 # ----------------------------------------------------------------------- sample / interpolate ----
 @pytest.mark.parametrize("W,H,ow,oh", [(1920, 1080, 1072, 608), (640, 360, 368, 208),
                                        (1000, 500, 300, 200), (333, 211, 100, 77)])
