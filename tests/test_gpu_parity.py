@@ -389,7 +389,10 @@ def test_gnomonic_vs_oracle(dev, fov, oracle, W, H, tw, th):
         proj.GnomonicProjection(out, tw, th, tw * 4, src, W, H, W * 4, cx, cy)
         got = dev.m.copy_to_host(np.empty((th, tw, 4), np.uint8), out)
         want = oracle.gnomonic(frame, tw, th, cx, cy)
-        worst = max(worst, _gather_mismatch(got, want, frame) / float(tw * th))
+        bad = _gather_mismatch(got, want, frame)
+        print("gnomonic %dx%d -> %dx%d view (%.2f, %.2f): %d of %d pixels differ" % (
+            W, H, tw, th, cx, cy, bad, tw * th))
+        worst = max(worst, bad / float(tw * th))
     assert worst <= 1e-3, worst
 
 
