@@ -100,7 +100,7 @@ struct __align__(16) SampleRow {
 #define FOV360_SAMPLE_MIN_CTAS 5
 #endif
 template <int kSampleRows>
-__global__ void __launch_bounds__(32 * kSampleWarps, kSampleRows == 4 ? FOV360_SAMPLE_MIN_CTAS : 1)
+__global__ void __launch_bounds__(32 * kSampleWarps, FOV360_SAMPLE_MIN_CTAS)
     sat_sample_rect_kernel(const SampleArgs a,
                                                                             const GazeBatch g) {
   __shared__ SampleRow srow[kSampleWarps * kSampleRows];
@@ -848,19 +848,12 @@ cudaError_t launch_sat_sample_rect(const LaunchCtx &lc, int n, uint8_t *out, siz
   a.o_linesize_px = out_linesize / 4;  // :153
   a.W = W;
   a.H = H;
-  static const int rows_per_warp = [] {
-    const char *e = getenv("FOV360_SAMPLE_ROWS");
-    return e ? atoi(e) : 4;
-  }();
-  const int rpw = rows_per_warp == 8 ? 8 : 4;
+  constexpr int kRows = 4;  // reduced rows per warp: 5 edges x 3 words in flight per lane
   const dim3 grid((ow + kSampleCols - 1) / kSampleCols,
-                  (oh + kSampleWarps * rpw - 1) / (kSampleWarps * rpw), n),
+                  (oh + kSampleWarps * kRows - 1) / (kSampleWarps * kRows), n),
       block(32, kSampleWarps);
   KernelScope ks(lc, "sat_sample_rect");
-  if (rpw == 8)
-    sat_sample_rect_kernel<8><<<grid, block, 0, lc.stream>>>(a, gaze);
-  else
-    sat_sample_rect_kernel<4><<<grid, block, 0, lc.stream>>>(a, gaze);
+  sat_sample_rect_kernel<kRows><<<grid, block, 0, lc.stream>>>(a, gaze);
   return cudaGetLastError();
 }
 

@@ -21,9 +21,10 @@
 //                 decoupled look-back: a warp publishes its band aggregate
 //                 G_b(x) = T_{b+1}(x) - T_b(x) as soon as its left carry is known (state AGG),
 //                 walks up the column adding aggregates until it meets a strip whose T is final
-//                 (state INC), and then publishes its own inclusive value.  The inclusive value
-//                 T_{b+1}(x) IS the last SAT row of the tile, so it is written straight into the
-//                 output and costs no extra traffic; only the aggregates use scratch memory.
+//                 (state INC), and then publishes its own inclusive value T_{b+1}(x) (the last
+//                 SAT row of the tile) in the same scratch slot.
+// Both carries travel as self-validating 16-byte units {three words, tag} written and polled with
+// single-copy-atomic 128-bit accesses: no release fence, no separate flag (see ld_unit below).
 // Tiles are handed out through an atomic ticket in (band, frame, strip) order, so every tile a
 // CTA waits for has an earlier ticket and is already resident or finished: no deadlock, no
 // co-residency assumption beyond what a running CTA guarantees.
@@ -56,7 +57,6 @@ struct OnePassArgs {
   int W, H, linesize;
   int n, R, nb, ns, nsc;  // frames, band rows, bands, warp strips, CTA strips
   uint32_t epoch, total_tiles;
-  int policy;  // L2 eviction-hint experiment selector (FOV360_SAT_POLICY)
   uint32_t *counters;  // [0] ticket, [1] finished CTAs
   uint4 *rowagg;       // [tile][kMaxBandRows]  {r, g, b, epoch}: per-row sums of a CTA tile
   uint4 *colagg;       // [tile][NW][4][32]     {v0, v1, v2, epoch << 2 | state}: column carry
@@ -109,14 +109,12 @@ __device__ __forceinline__ uint4 load_row4(const uint8_t *row, int x0, int W, ui
   return v;
 }
 
-// STORE: 1 = cp.async.bulk (TMA) store of the staged row, 2 = staged row re-read lane-contiguously
-// and written with three fully coalesced 16-byte stores per lane.
-template <int STORE, int MIN_CTAS, int kLoadDepth, int U>
+// kLoadDepth rows are in flight per lane while the strip is reduced, U while it is scanned.
+template <int MIN_CTAS, int kLoadDepth, int U>
 __global__ void __launch_bounds__(kMaxWarps * 32, MIN_CTAS) sat_onepass_kernel(const OnePassArgs a) {
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ uint32_t s_ticket;
-  constexpr bool TMA_STORE = STORE == 1;
-  constexpr int kBufs = TMA_STORE ? kStageBufs : 2;
+  constexpr int kBufs = kStageBufs;
   const int NW = blockDim.x >> 5;
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
@@ -149,13 +147,6 @@ __global__ void __launch_bounds__(kMaxWarps * 32, MIN_CTAS) sat_onepass_kernel(c
   uint64_t pol_keep, pol_stream;
   asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol_keep));
   asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_stream));
-  if (a.policy) {
-    uint64_t pol_normal;
-    asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pol_normal));
-    if (a.policy == 1) pol_keep = pol_normal;
-    if (a.policy == 2) pol_keep = pol_normal, pol_stream = pol_normal;
-    if (a.policy == 3) pol_stream = pol_normal;
-  }
 
   // ---- phase A: read the strip once; column sums per lane, row sums per row ------------------
   // Sums of at most 64 rows (columns) or 128 pixels (rows) of bytes fit 16 bits, so two channels
@@ -369,47 +360,30 @@ __global__ void __launch_bounds__(kMaxWarps * 32, MIN_CTAS) sat_onepass_kernel(c
           uint32_t *drow = sat + ((size_t)(y + u) * a.W) * 3;
           uint8_t *sb = my_stage + (size_t)buf * kRowBytes;
           uint4 *sd = reinterpret_cast<uint4 *>(sb + lane * 48);
-          if (TMA_STORE) {
-            // stage the 1536-byte row segment, then one bulk async store per row
-            if (lane == 0)
-              asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(kBufs - 1) : "memory");
-            __syncwarp();
-            sd[0] = make_uint4(acc[0], acc[1], acc[2], acc[3]);
-            sd[1] = make_uint4(acc[4], acc[5], acc[6], acc[7]);
-            sd[2] = make_uint4(acc[8], acc[9], acc[10], acc[11]);
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            __syncwarp();
-            if (lane == 0) {
-              asm volatile(
-                  "cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;\n\t"
-                  "cp.async.bulk.commit_group;" ::"l"(drow + (size_t)strip * kStripPx * 3),
-                  "r"(smem_u32(sb)), "r"(strip_px * 12), "l"(policy)
-                  : "memory");
-            }
-            buf = (buf + 1 == kBufs) ? 0 : buf + 1;
-          } else {
-            // transpose through shared memory so that each store instruction of the warp covers
-            // 512 contiguous bytes (lane-strided 48-byte stores run at ~60 % of this)
-            sd[0] = make_uint4(acc[0], acc[1], acc[2], acc[3]);
-            sd[1] = make_uint4(acc[4], acc[5], acc[6], acc[7]);
-            sd[2] = make_uint4(acc[8], acc[9], acc[10], acc[11]);
-            __syncwarp();
-            const uint4 *sl = reinterpret_cast<const uint4 *>(sb) + lane;
-            uint4 *d = reinterpret_cast<uint4 *>(drow + (size_t)strip * kStripPx * 3) + lane;
-            const int n16 = strip_px * 3 / 4;  // 16-byte words in this row segment
-#pragma unroll
-            for (int k = 0; k < 3; ++k)
-              if (k * 32 + lane < n16) __stcs(d + k * 32, sl[k * 32]);
-            buf ^= 1;
+          // stage the 1536-byte row segment, then one bulk async store per row (lane-strided
+          // 48-byte register stores reach ~60 % of the bandwidth of 512-byte-contiguous ones)
+          if (lane == 0)
+            asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(kBufs - 1) : "memory");
+          __syncwarp();
+          sd[0] = make_uint4(acc[0], acc[1], acc[2], acc[3]);
+          sd[1] = make_uint4(acc[4], acc[5], acc[6], acc[7]);
+          sd[2] = make_uint4(acc[8], acc[9], acc[10], acc[11]);
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          __syncwarp();
+          if (lane == 0) {
+            asm volatile(
+                "cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;\n\t"
+                "cp.async.bulk.commit_group;" ::"l"(drow + (size_t)strip * kStripPx * 3),
+                "r"(smem_u32(sb)), "r"(strip_px * 12), "l"(policy)
+                : "memory");
           }
+          buf = (buf + 1 == kBufs) ? 0 : buf + 1;
         }
       }
     }
-    if (TMA_STORE) {
-      // shared memory must outlive the in-flight bulk reads
-      if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-      __syncwarp();
-    }
+    // shared memory must outlive the in-flight bulk reads
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    __syncwarp();
   }
 
   // ---- the last CTA to finish re-arms the ticket counter for the next launch ------------------
@@ -492,8 +466,6 @@ cudaError_t launch_sat_onepass(const LaunchCtx &lc, int n, uint32_t *sat, size_t
   a.nsc = p.nsc;
   a.epoch = epoch;
   a.total_tiles = (uint32_t)((size_t)n * p.nb * p.nsc);
-  static const int policy = env_int("FOV360_SAT_POLICY", 0);
-  a.policy = policy;
   a.counters = reinterpret_cast<uint32_t *>(base + p.off_counters);
   a.rowagg = reinterpret_cast<uint4 *>(base + p.off_rowagg);
   a.colagg = reinterpret_cast<uint4 *>(base + p.off_colagg);
@@ -501,34 +473,19 @@ cudaError_t launch_sat_onepass(const LaunchCtx &lc, int n, uint32_t *sat, size_t
   a.trace = g_sat_trace;
 #endif
 
-  static const bool tma_store = env_int("FOV360_SAT_TMA_STORE", 1) != 0;
-  const size_t carry_smem = (size_t)(p.NW * p.R + p.R) * 16;
-  static const int pad_smem = env_int("FOV360_SAT_PAD_SMEM", 0);  // occupancy experiments
-  const size_t smem = carry_smem + (size_t)p.NW * (tma_store ? kStageBufs : 2) * kRowBytes + pad_smem;
-  const int max_smem = 200 * 1024;
+  const size_t smem = (size_t)(p.NW * p.R + p.R) * 16 + (size_t)p.NW * kStageBufs * kRowBytes;
+  constexpr int kMaxSmem = (kMaxWarps * kMaxBandRows + kMaxBandRows) * 16 +
+                           kMaxWarps * kStageBufs * kRowBytes;
+  // 3 CTAs of 256 threads per SM bound the registers at 80; the 192-thread CTAs 8K frames use then
+  // run 4 per SM.  8 rows in flight per lane while reducing, 4 while scanning.
+  auto kernel = sat_onepass_kernel<3, 8, 4>;
+  static bool attr_set[64] = {};
+  if (!attr_set[lc.device & 63]) {
+    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+    attr_set[lc.device & 63] = true;
+  }
   KernelScope ks(lc, "sat_onepass");
-  static const int variant = env_int("FOV360_SAT_VARIANT", 0);
-  static const int carveout = env_int("FOV360_SAT_CARVEOUT", -1);  // % of the L1/shared array
-#define FOV_LAUNCH(TMA, MINC, DEPTH, UU)                                                          \
-  do {                                                                                             \
-    cudaFuncSetAttribute(sat_onepass_kernel<TMA, MINC, DEPTH, UU>,                                 \
-                         cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);                   \
-    if (carveout >= 0)                                                                             \
-      cudaFuncSetAttribute(sat_onepass_kernel<TMA, MINC, DEPTH, UU>,                               \
-                           cudaFuncAttributePreferredSharedMemoryCarveout, carveout);              \
-    sat_onepass_kernel<TMA, MINC, DEPTH, UU><<<a.total_tiles, p.NW * 32, smem, lc.stream>>>(a);    \
-  } while (0)
-  if (tma_store)
-    FOV_LAUNCH(1, 3, 8, 4);
-  else if (variant == 1)
-    FOV_LAUNCH(2, 4, 8, 4);
-  else if (variant == 2)
-    FOV_LAUNCH(2, 5, 8, 4);
-  else if (variant == 3)
-    FOV_LAUNCH(2, 4, 16, 4);
-  else
-    FOV_LAUNCH(2, 3, 8, 4);
-#undef FOV_LAUNCH
+  kernel<<<a.total_tiles, p.NW * 32, smem, lc.stream>>>(a);
   return cudaGetLastError();
 }
 
