@@ -17,6 +17,7 @@ from .host import (  # noqa: F401
     Projections,
     SATDecoder,
     SATEncoder,
+    VideoFrameConverter,
     reduced_dim,
 )
 

@@ -60,6 +60,11 @@ PROTOTYPES = {
     "fov_img_logpolar_blur": (_i, [_vp, _vp, _i, _i, _i, _vp]),
     "fov_gnomonic": (_i, [_vp, _vp, _i, _i, _i, _vp, _i, _i, _i, _f, _f]),
     "fov_sat_interpolate_gnomonic": (_i, [_vp, _vp, _i, _i, _vp, _i, _i, _i, _i, _f, _f, _f, _f]),
+    "fov_rgb0_to_yuv420p": (_i, [_vp, _vp, _i, _vp, _i, _vp, _i, _vp, _i, _i, _i]),
+    "fov_rgb0_to_nv12": (_i, [_vp, _vp, _i, _vp, _i, _vp, _i, _i, _i]),
+    "fov_rgb0_to_yuv420p_batched": (_i, [_vp, _i, _vp, _sz, _i, _vp, _vp, _sz, _i, _vp, _sz, _i,
+                                         _i, _i]),
+    "fov_rgb0_to_nv12_batched": (_i, [_vp, _i, _vp, _sz, _i, _vp, _sz, _i, _vp, _sz, _i, _i, _i]),
     "fov_reduced_dim": (_i, [_i]),
 }
 

@@ -735,6 +735,65 @@ int fov_img_logpolar_blur(fov_ctx *ctx, uint8_t *out, int ow, int oh, int linesi
   return FOV_OK;
 }
 
+// ---- VideoEncoder colour conversion ------------------------------------------------------------
+
+namespace {
+int yuv_convert(fov_ctx *ctx, const char *who, bool nv12, int n, uint8_t *y, size_t y_stride,
+                int y_ls, uint8_t *u, int u_ls, uint8_t *v, int v_ls, size_t c_stride,
+                const uint8_t *src, size_t src_stride, int src_ls, int W, int H) {
+  FOV_REQUIRE_CTX(ctx);
+  const int cw = nv12 ? W : W / 2;  // bytes per chroma row
+  if (!y || !u || (!nv12 && !v) || !src || n < 1 || W <= 0 || H <= 0 || y_ls < W || u_ls < cw ||
+      (!nv12 && v_ls < cw) || src_ls < 4 * W || (src_ls & 3) || ((uintptr_t)src & 3) ||
+      (src_stride & 3))
+    return fail(ctx, FOV_ERR_INVALID, std::string(who) + ": invalid arguments");
+  if ((W & 1) || (H & 1) || H < 8)
+    return fail(ctx, FOV_ERR_UNSUPPORTED,
+                std::string(who) + ": width and height must be even and height >= 8");
+  DeviceGuard g(ctx);
+  for (int f0 = 0; f0 < n; f0 += 65535) {  // gridDim.z limit
+    const int nf = std::min(n - f0, 65535);
+    FOV_CUDA(ctx,
+             launch_rgb0_to_yuv(ctx->lc(), nv12, nf, y + (size_t)f0 * y_stride, y_stride, y_ls,
+                                u + (size_t)f0 * c_stride, u_ls,
+                                v ? v + (size_t)f0 * c_stride : nullptr, v_ls, c_stride,
+                                src + (size_t)f0 * src_stride, src_stride, src_ls, W, H),
+             who);
+  }
+  return FOV_OK;
+}
+}  // namespace
+
+int fov_rgb0_to_yuv420p(fov_ctx *ctx, uint8_t *y, int y_linesize, uint8_t *u, int u_linesize,
+                        uint8_t *v, int v_linesize, const uint8_t *src, int src_linesize,
+                        int width, int height) {
+  return yuv_convert(ctx, "fov_rgb0_to_yuv420p", false, 1, y, 0, y_linesize, u, u_linesize, v,
+                     v_linesize, 0, src, 0, src_linesize, width, height);
+}
+
+int fov_rgb0_to_nv12(fov_ctx *ctx, uint8_t *y, int y_linesize, uint8_t *uv, int uv_linesize,
+                     const uint8_t *src, int src_linesize, int width, int height) {
+  return yuv_convert(ctx, "fov_rgb0_to_nv12", true, 1, y, 0, y_linesize, uv, uv_linesize, nullptr,
+                     0, 0, src, 0, src_linesize, width, height);
+}
+
+int fov_rgb0_to_yuv420p_batched(fov_ctx *ctx, int n, uint8_t *y, size_t y_stride, int y_linesize,
+                                uint8_t *u, uint8_t *v, size_t chroma_stride, int chroma_linesize,
+                                const uint8_t *src, size_t src_stride, int src_linesize, int width,
+                                int height) {
+  return yuv_convert(ctx, "fov_rgb0_to_yuv420p_batched", false, n, y, y_stride, y_linesize, u,
+                     chroma_linesize, v, chroma_linesize, chroma_stride, src, src_stride,
+                     src_linesize, width, height);
+}
+
+int fov_rgb0_to_nv12_batched(fov_ctx *ctx, int n, uint8_t *y, size_t y_stride, int y_linesize,
+                             uint8_t *uv, size_t uv_stride, int uv_linesize, const uint8_t *src,
+                             size_t src_stride, int src_linesize, int width, int height) {
+  return yuv_convert(ctx, "fov_rgb0_to_nv12_batched", true, n, y, y_stride, y_linesize, uv,
+                     uv_linesize, nullptr, 0, uv_stride, src, src_stride, src_linesize, width,
+                     height);
+}
+
 int fov_reduced_dim(int full_dim) {
   // 16 * ceil(dim / 1.8 / 16), run_satlogrectilinear.cc:113-114
   return 16 * (int)std::ceil(full_dim / 1.8 / 16);

@@ -1,0 +1,155 @@
+// RGB0 -> YUV420P / NV12 on the device.
+//
+// Replaces the colour conversion inside VideoEncoder::EncodeFrame (video_encoder.cc:380-398):
+// the reference copies the foveated RGB0 buffer to the host, runs
+// sws_getContext(w, h, RGB0, w, h, YUV420P, SWS_BILINEAR) + sws_scale on the CPU and uploads the
+// planes again with av_hwframe_transfer_data.  Here the planes are produced where the reduced
+// buffer already lives, straight into the device surface the hardware encoder reads (planar
+// YUV420P = the reference's sw_format, video_encoder.cc:549; NV12 = NVENC's native layout, the
+// same samples with U and V interleaved).
+//
+// The arithmetic is libswscale's C path, integer and exact (FFmpeg 4.2 libswscale: input.c:252-345,
+// swscale.c:96-122, output.c:380-403, utils.c:403-418,807-816; the parity tests pin it to golden
+// vectors produced by a real libswscale):
+//   luma    Y  = clip8((min(2 * ((RY r + GY g + BY b + (32 << 14) + 256) >> 9), 32767) + 64) >> 7)
+//   chroma  c15(row, pair) = min(2 * ((RU (r0+r1) + GU (g0+g1) + BU (b0+b1) + (256 << 15) + 512) >> 10), 32767)
+//           U  = clip8(((64 << 12) + 512 c15(2j-1) + 1536 c15(2j) + 1536 c15(2j+1) + 512 c15(2j+2)) >> 19)
+// with rows outside the frame replicating the edge row.  HBM traffic: 4 B/px read, 1.5 B/px
+// written - 6 % of the foveation pipeline's bytes at the same frame size, so it stays a separate
+// kernel behind sample_rect (whose boxes do not line up with the 2x4 chroma footprint).
+#include "fov360_internal.h"
+
+namespace fov {
+namespace {
+
+constexpr int kRY = 8414, kGY = 16519, kBY = 3208;
+constexpr int kRU = -4865, kGU = -9528, kBU = 14392;
+constexpr int kRV = 14392, kGV = -12061, kBV = -2332;
+
+struct YuvArgs {
+  uint8_t *y, *u, *v;  // v unused for NV12 (u = the interleaved plane)
+  const uint8_t *src;
+  size_t y_stride, c_stride, src_stride;  // per-frame strides in bytes
+  int y_ls, c_ls, v_ls, src_ls;           // linesizes in bytes (c_ls: U or interleaved plane)
+  int W, H;
+};
+
+__device__ __forceinline__ int clip8(int v) { return min(max(v, 0), 255); }
+__device__ __forceinline__ int widen15(int v14) { return min(v14 * 2, 32767); }
+
+__device__ __forceinline__ int luma8(uint32_t p) {
+  const int r = p & 0xff, g = (p >> 8) & 0xff, b = (p >> 16) & 0xff;
+  const int y14 = (kRY * r + kGY * g + kBY * b + (32 << 14) + 256) >> 9;
+  return clip8((widen15(y14) + 64) >> 7);
+}
+
+// 15-bit chroma of one horizontal pixel pair
+__device__ __forceinline__ void chroma15(uint32_t p0, uint32_t p1, int &u15, int &v15) {
+  const int r = (p0 & 0xff) + (p1 & 0xff);
+  const int g = ((p0 >> 8) & 0xff) + ((p1 >> 8) & 0xff);
+  const int b = ((p0 >> 16) & 0xff) + ((p1 >> 16) & 0xff);
+  constexpr int rnd = (256 << 15) + 512;
+  u15 = widen15((kRU * r + kGU * g + kBU * b + rnd) >> 10);
+  v15 = widen15((kRV * r + kGV * g + kBV * b + rnd) >> 10);
+}
+
+// One thread: 4 consecutive pixels x 2 rows of luma, 2 chroma samples.  Block (32, 8): the
+// one-row halo above and below a thread's row pair is its neighbour's row pair, so the second
+// read of a row comes from L1.
+template <bool kNV12>
+__global__ void __launch_bounds__(256) rgb0_to_yuv_kernel(const YuvArgs a) {
+  const int x0 = (blockIdx.x * 32 + threadIdx.x) * 4;
+  const int j = blockIdx.y * 8 + threadIdx.y;  // chroma row
+  const int W = a.W, H = a.H;
+  if (x0 >= W || 2 * j >= H) return;
+  const int f = blockIdx.z;
+  const uint8_t *src = a.src + (size_t)f * a.src_stride;
+  const bool full = x0 + 4 <= W;  // false only for the last thread of a row when W % 4 == 2
+  const bool vec = full && ((reinterpret_cast<uintptr_t>(src) | (uintptr_t)a.src_ls) & 15) == 0;
+
+  uint32_t px[4][4];  // [source row 2j-1 .. 2j+2][pixel]
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int yy = min(max(2 * j - 1 + k, 0), H - 1);
+    const uint8_t *row = src + (size_t)yy * a.src_ls + (size_t)x0 * 4;
+    if (vec) {
+      const uint4 q = __ldg(reinterpret_cast<const uint4 *>(row));
+      px[k][0] = q.x, px[k][1] = q.y, px[k][2] = q.z, px[k][3] = q.w;
+    } else {
+      const uint32_t *r32 = reinterpret_cast<const uint32_t *>(row);
+      px[k][0] = __ldg(r32), px[k][1] = __ldg(r32 + 1);
+      px[k][2] = full ? __ldg(r32 + 2) : 0u, px[k][3] = full ? __ldg(r32 + 3) : 0u;
+    }
+  }
+
+  // luma: source rows 2j and 2j+1 are px[1] and px[2]
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    uint8_t *yrow = a.y + (size_t)f * a.y_stride + (size_t)(2 * j + r) * a.y_ls + x0;
+    const int l0 = luma8(px[1 + r][0]), l1 = luma8(px[1 + r][1]);
+    const int l2 = luma8(px[1 + r][2]), l3 = luma8(px[1 + r][3]);
+    if (full && (reinterpret_cast<uintptr_t>(yrow) & 3) == 0) {
+      *reinterpret_cast<uint32_t *>(yrow) = (uint32_t)l0 | (l1 << 8) | (l2 << 16) | (l3 << 24);
+    } else {
+      yrow[0] = (uint8_t)l0, yrow[1] = (uint8_t)l1;
+      if (full) yrow[2] = (uint8_t)l2, yrow[3] = (uint8_t)l3;
+    }
+  }
+
+  // chroma: two pairs, 4 vertical taps each
+  int su[2] = {64 << 12, 64 << 12}, sv[2] = {64 << 12, 64 << 12};
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int tap = (k == 0 || k == 3) ? 512 : 1536;
+#pragma unroll
+    for (int p = 0; p < 2; ++p) {
+      int cu, cv;
+      chroma15(px[k][2 * p], px[k][2 * p + 1], cu, cv);
+      su[p] += tap * cu;
+      sv[p] += tap * cv;
+    }
+  }
+  const int u0 = clip8(su[0] >> 19), u1 = clip8(su[1] >> 19);
+  const int v0 = clip8(sv[0] >> 19), v1 = clip8(sv[1] >> 19);
+  const int cx = x0 / 2;
+  if (kNV12) {
+    uint8_t *c = a.u + (size_t)f * a.c_stride + (size_t)j * a.c_ls + (size_t)cx * 2;
+    if (full && (reinterpret_cast<uintptr_t>(c) & 3) == 0) {
+      *reinterpret_cast<uint32_t *>(c) = (uint32_t)u0 | (v0 << 8) | (u1 << 16) | (v1 << 24);
+    } else {
+      c[0] = (uint8_t)u0, c[1] = (uint8_t)v0;
+      if (full) c[2] = (uint8_t)u1, c[3] = (uint8_t)v1;
+    }
+  } else {
+    uint8_t *up = a.u + (size_t)f * a.c_stride + (size_t)j * a.c_ls + cx;
+    uint8_t *vp = a.v + (size_t)f * a.c_stride + (size_t)j * a.v_ls + cx;
+    if (full && ((reinterpret_cast<uintptr_t>(up) | reinterpret_cast<uintptr_t>(vp)) & 1) == 0) {
+      *reinterpret_cast<uint16_t *>(up) = (uint16_t)(u0 | (u1 << 8));
+      *reinterpret_cast<uint16_t *>(vp) = (uint16_t)(v0 | (v1 << 8));
+    } else {
+      up[0] = (uint8_t)u0, vp[0] = (uint8_t)v0;
+      if (full) up[1] = (uint8_t)u1, vp[1] = (uint8_t)v1;
+    }
+  }
+}
+
+}  // namespace
+
+cudaError_t launch_rgb0_to_yuv(const LaunchCtx &lc, bool nv12, int n, uint8_t *y, size_t y_stride,
+                               int y_ls, uint8_t *u, int u_ls, uint8_t *v, int v_ls, size_t c_stride,
+                               const uint8_t *src, size_t src_stride, int src_ls, int W, int H) {
+  YuvArgs a;
+  a.y = y, a.u = u, a.v = v, a.src = src;
+  a.y_stride = y_stride, a.c_stride = c_stride, a.src_stride = src_stride;
+  a.y_ls = y_ls, a.c_ls = u_ls, a.v_ls = v_ls, a.src_ls = src_ls;
+  a.W = W, a.H = H;
+  const dim3 grid((W + 127) / 128, (H / 2 + 7) / 8, n), block(32, 8);
+  KernelScope ks(lc, nv12 ? "rgb0_to_nv12" : "rgb0_to_yuv420p");
+  if (nv12)
+    rgb0_to_yuv_kernel<true><<<grid, block, 0, lc.stream>>>(a);
+  else
+    rgb0_to_yuv_kernel<false><<<grid, block, 0, lc.stream>>>(a);
+  return cudaGetLastError();
+}
+
+}  // namespace fov

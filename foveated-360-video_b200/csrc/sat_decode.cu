@@ -365,6 +365,69 @@ __device__ __forceinline__ uint32_t lerp_px(const float4 v, const float4 d, floa
                    trunc_bits(lerp_rn(v.z, d.z, t)));
 }
 
+// Packed fp32 pairs (sm_100 FMUL2 / FADD2): two independent IEEE single operations per instruction,
+// each rounded exactly like its scalar form.  ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into
+// FFMA2 even though both carry an explicit rounding mode; a multiply with .ftz is never contracted
+// with an add without it, and no operand or product here is subnormal (bytes, ratios k/n, and
+// their differences are 0 or >= 2^-17 in magnitude), so .ftz changes nothing.
+using f32x2 = unsigned long long;
+__device__ __forceinline__ f32x2 pack2(float lo, float hi) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack2(f32x2 v, uint32_t &lo, uint32_t &hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=r"(lo), "=r"(hi) : "l"(v));
+}
+__device__ __forceinline__ f32x2 mul2_rn(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("mul.rn.ftz.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ f32x2 add2_rn(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ f32x2 sub2_rn(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+// both halves: low mantissa bits of v + 2^23 rounded toward zero (trunc_bits)
+__device__ __forceinline__ f32x2 trunc_bits2(f32x2 v) {
+  f32x2 r;
+  asm("add.rz.f32x2 %0, %1, %2;" : "=l"(r) : "l"(v), "l"(0x4B0000004B000000ull));
+  return r;
+}
+// byte C of two pixels as a float pair (byte_to_float twice, one packed subtract)
+template <int C>
+__device__ __forceinline__ f32x2 bytes_to_float2(uint32_t a, uint32_t b) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};"
+      : "=l"(r)
+      : "r"(__byte_perm(a, 0x4B000000u, 0x7440u | C)), "r"(__byte_perm(b, 0x4B000000u, 0x7440u | C)));
+  return sub2_rn(r, 0x4B0000004B000000ull);
+}
+// lerp_px on a staged column: v = {V.x, V.y | V.z, V.w}, d likewise, t2 = {t, t}.  The .w halves
+// (the exact-hit samples' 4th bytes) ride through the arithmetic unused.
+__device__ __forceinline__ uint32_t lerp_px2(const ulonglong2 v, const ulonglong2 d, f32x2 t2) {
+  uint32_t c0, c1, c2, c3;
+  unpack2(trunc_bits2(add2_rn(v.x, mul2_rn(d.x, t2))), c0, c1);
+  unpack2(trunc_bits2(add2_rn(v.y, mul2_rn(d.y, t2))), c2, c3);
+  return pack_rgb0(c0, c1, c2);
+}
+
+// One pixel of the periphery path from its staged column: colour from V + D * t, 4th byte from
+// V.w (exact hit on the column itself) or D.w (on the column to the right).
+__device__ __forceinline__ uint32_t staged_px(const ulonglong2 v, const ulonglong2 d, float t,
+                                              uint32_t keep_lo, uint32_t keep_hi) {
+  uint32_t vz, vw, dz, dw;
+  unpack2(v.y, vz, vw);
+  unpack2(d.y, dz, dw);
+  return lerp_px2(v, d, pack2(t, t)) | (vw & keep_lo) | (dw & keep_hi);
+}
+
 // interpolate_rect, one warp = 128 columns x kInterpRows rows.
 //
 // Everything that depends on x only (table entry, wrap, border fix-ups, clamped reduced columns,
@@ -512,7 +575,8 @@ __global__ void __launch_bounds__(32 * kInterpWarps, FOV360_INTERP_MIN_CTAS)
     }
     const uint32_t *col_left = red + xlo[0];  // left tap of pixel 0 (when it is a ratio-one pixel)
     const bool all_one = __all_sync(0xffffffffu, one[0] && one[1] && one[2] && one[3]);
-    TapPair tp[kInterpPx] = {}, tpl = {};
+    TapPair tpl = {};
+    f32x2 tp2[3][2] = {}, td2[3][2] = {};  // p and q - p of channel c, pixels (h, h + 2)
     int r = 0;
     while (r < nrows) {
       const RowSel rs = rowsel[warp][r];
@@ -546,54 +610,78 @@ __global__ void __launch_bounds__(32 * kInterpWarps, FOV360_INTERP_MIN_CTAS)
         }
         r += nb;
       } else {
+        // Packed form: half h of channel c holds pixels (h, h + 2) of the lane, so the left
+        // neighbours of pixels (1, 3) are the pair of pixels (0, 2) itself.
         if (rs.info & 1) {  // warp-uniform: new reduced row pair
+          uint32_t rp[kInterpPx], rq[kInterpPx];
 #pragma unroll
-          for (int k = 0; k < kInterpPx; ++k)
-            convert_tap_pair(tp[k], __ldg(col[k] + rs.off_lo), __ldg(col[k] + rs.off_hi));
+          for (int k = 0; k < kInterpPx; ++k) {
+            rp[k] = __ldg(col[k] + rs.off_lo);
+            rq[k] = __ldg(col[k] + rs.off_hi);
+          }
           if (need_left) convert_tap_pair(tpl, __ldg(col_left + rs.off_lo), __ldg(col_left + rs.off_hi));
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            tp2[0][h] = bytes_to_float2<0>(rp[h], rp[h + 2]);
+            tp2[1][h] = bytes_to_float2<1>(rp[h], rp[h + 2]);
+            tp2[2][h] = bytes_to_float2<2>(rp[h], rp[h + 2]);
+            td2[0][h] = sub2_rn(bytes_to_float2<0>(rq[h], rq[h + 2]), tp2[0][h]);
+            td2[1][h] = sub2_rn(bytes_to_float2<1>(rq[h], rq[h + 2]), tp2[1][h]);
+            td2[2][h] = sub2_rn(bytes_to_float2<2>(rq[h], rq[h + 2]), tp2[2][h]);
+          }
         }
-        float v[kInterpPx][3];
+        {
+          const f32x2 ty2 = pack2(rs.ty, rs.ty);
+          f32x2 v2[3][2];
 #pragma unroll
-        for (int k = 0; k < kInterpPx; ++k)
+          for (int c = 0; c < 3; ++c)
 #pragma unroll
-          for (int c = 0; c < 3; ++c) v[k][c] = lerp_rn(tp[k].p[c], tp[k].d[c], rs.ty);
-        uint32_t px[kInterpPx];
-        if (all_one) {  // warp-uniform: right of the gaze every pixel is mix(l, r, 1) = l + (r - l)
-          float l[3];
-#pragma unroll
-          for (int c = 0; c < 3; ++c) l[c] = lerp_rn(tpl.p[c], tpl.d[c], rs.ty);
-#pragma unroll
-          for (int k = 0; k < kInterpPx; ++k) {
-            float o[3];
+            for (int h = 0; h < 2; ++h) v2[c][h] = add2_rn(tp2[c][h], mul2_rn(td2[c][h], ty2));
+          uint32_t bits[kInterpPx][3];
+          if (all_one) {  // warp-uniform: every pixel is mix(l, r, 1) = l + (r - l)
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
-              o[c] = __fadd_rn(l[c], __fsub_rn(v[k][c], l[c]));  // (r - l) * 1.0f is exact
-              l[c] = v[k][c];
+              const float lc = lerp_rn(tpl.p[c], tpl.d[c], rs.ty);
+              uint32_t v1, v3;
+              unpack2(v2[c][1], v1, v3);
+              const f32x2 l02 = pack2(lc, __uint_as_float(v1));  // left of pixels (0, 2)
+              const f32x2 o02 = trunc_bits2(add2_rn(l02, sub2_rn(v2[c][0], l02)));
+              const f32x2 o13 = trunc_bits2(add2_rn(v2[c][0], sub2_rn(v2[c][1], v2[c][0])));
+              unpack2(o02, bits[0][c], bits[2][c]);
+              unpack2(o13, bits[1][c], bits[3][c]);
             }
-            px[k] = pack_rgb0(trunc_bits(o[0]), trunc_bits(o[1]), trunc_bits(o[2]));
-          }
-        } else if (need_left) {  // warp-uniform: the warp that holds the gaze column
-          float l[3];
+          } else if (need_left) {  // warp-uniform: the warp that holds the gaze column
+            float l[3];
 #pragma unroll
-          for (int c = 0; c < 3; ++c) l[c] = lerp_rn(tpl.p[c], tpl.d[c], rs.ty);
-#pragma unroll
-          for (int k = 0; k < kInterpPx; ++k) {
-            float o[3];
+            for (int c = 0; c < 3; ++c) l[c] = lerp_rn(tpl.p[c], tpl.d[c], rs.ty);
+            uint32_t vb[kInterpPx][3];
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
-              o[c] = one[k] ? __fadd_rn(l[c], __fsub_rn(v[k][c], l[c])) : v[k][c];
-              l[c] = v[k][c];
+              unpack2(v2[c][0], vb[0][c], vb[2][c]);
+              unpack2(v2[c][1], vb[1][c], vb[3][c]);
             }
-            px[k] = pack_rgb0(trunc_bits(o[0]), trunc_bits(o[1]), trunc_bits(o[2]));
-          }
-        } else {
 #pragma unroll
-          for (int k = 0; k < kInterpPx; ++k)
-            px[k] = pack_rgb0(trunc_bits(v[k][0]), trunc_bits(v[k][1]), trunc_bits(v[k][2]));
+            for (int k = 0; k < kInterpPx; ++k)
+#pragma unroll
+              for (int c = 0; c < 3; ++c) {
+                const float vk = __uint_as_float(vb[k][c]);
+                bits[k][c] = trunc_bits(one[k] ? __fadd_rn(l[c], __fsub_rn(vk, l[c])) : vk);
+                l[c] = vk;
+              }
+          } else {
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+              unpack2(trunc_bits2(v2[c][0]), bits[0][c], bits[2][c]);
+              unpack2(trunc_bits2(v2[c][1]), bits[1][c], bits[3][c]);
+            }
+          }
+          uint32_t px[kInterpPx];
+#pragma unroll
+          for (int k = 0; k < kInterpPx; ++k) px[k] = pack_rgb0(bits[k][0], bits[k][1], bits[k][2]);
+          store_row(px);
+          orow += W;
+          ++r;
         }
-        store_row(px);
-        orow += W;
-        ++r;
       }
     }
     return;
@@ -611,6 +699,17 @@ __global__ void __launch_bounds__(32 * kInterpWarps, FOV360_INTERP_MIN_CTAS)
       keep_hi[k] = (xex[k] >= 0 && xex[k] != xlo[k]) ? 0xff000000u : 0u;
       if (xhi[k] == xlo[k]) xr[k] = 0.0f;  // V + D * 0 = V: the selected column, exactly
     }
+    // In the periphery 4 consecutive pixels sit on at most two reduced columns - those of the
+    // lane's first and last pixel: pass 2 then reads 2 staged columns per row instead of 4 (the
+    // pass is bound by shared-memory bandwidth, not by issue slots).
+    bool use_b[kInterpPx];
+    bool two = true;
+#pragma unroll
+    for (int k = 1; k < kInterpPx - 1; ++k) {
+      use_b[k] = xlo[k] != xlo[0];
+      two = two && (xlo[k] == xlo[0] || xlo[k] == xlo[kInterpPx - 1]);
+    }
+    const bool two_cols = __all_sync(0xffffffffu, two);
     // lanes past the window repeat its last column: every V and D stays finite, and the D of the
     // last column (0, or never multiplied by a non-zero tx) needs no special case
     const uint32_t *rcol = red + cmin + min(lane, ncols - 1);
@@ -625,19 +724,22 @@ __global__ void __launch_bounds__(32 * kInterpWarps, FOV360_INTERP_MIN_CTAS)
         rawq[j] = __ldg(rcol + rs.off_hi);
       }
     };
+    // packed pass 1: {V.x, V.y} and {V.z, alpha} are the two 8-byte halves of the staged float4
     auto stage_row = [&](int j, const RowSel rs) {
-      const float v0 = lerp_rn(tp.p[0], tp.d[0], rs.ty);
-      const float v1 = lerp_rn(tp.p[1], tp.d[1], rs.ty);
+      const f32x2 ty2 = pack2(rs.ty, rs.ty);
+      const f32x2 v01 = add2_rn(pack2(tp.p[0], tp.p[1]), mul2_rn(pack2(tp.d[0], tp.d[1]), ty2));
       const float v2 = lerp_rn(tp.p[2], tp.d[2], rs.ty);
-      const float n0 = __shfl_down_sync(0xffffffffu, v0, 1);
-      const float n1 = __shfl_down_sync(0xffffffffu, v1, 1);
-      const float n2 = __shfl_down_sync(0xffffffffu, v2, 1);
-      // exact-hit rows: V.w carries the sample's 4th byte, D.w that of the column to the right
       const uint32_t alpha = rs.info >= 0 ? (rawp[j] & 0xff000000u) : 0u;
-      const uint32_t alpha_next = __shfl_down_sync(0xffffffffu, alpha, 1);
-      vs[j * 32 + lane] = make_float4(v0, v1, v2, __uint_as_float(alpha));
-      vs[(kInterpChunk + j) * 32 + lane] = make_float4(
-          __fsub_rn(n0, v0), __fsub_rn(n1, v1), __fsub_rn(n2, v2), __uint_as_float(alpha_next));
+      const f32x2 v2a = pack2(v2, __uint_as_float(alpha));
+      const f32x2 n01 = __shfl_down_sync(0xffffffffu, v01, 1);
+      const f32x2 n2a = __shfl_down_sync(0xffffffffu, v2a, 1);
+      uint32_t n2, alpha_next, d2;
+      unpack2(n2a, n2, alpha_next);
+      d2 = __float_as_uint(__fsub_rn(__uint_as_float(n2), v2));
+      ulonglong2 *dst = reinterpret_cast<ulonglong2 *>(vs);
+      dst[j * 32 + lane] = make_ulonglong2(v01, v2a);
+      dst[(kInterpChunk + j) * 32 + lane] =
+          make_ulonglong2(sub2_rn(n01, v01), pack2(__uint_as_float(d2), __uint_as_float(alpha_next)));
     };
     request(0);
     for (int r0 = 0; r0 < nrows; r0 += kInterpChunk) {
@@ -667,11 +769,24 @@ __global__ void __launch_bounds__(32 * kInterpWarps, FOV360_INTERP_MIN_CTAS)
 #pragma unroll
       for (int j = 0; j < kInterpChunk; ++j) {
         uint32_t px[kInterpPx];
+        if (two_cols) {  // warp-uniform: columns of pixels 1 and 2 are those of pixel 0 or pixel 3
+          const ulonglong2 va = *reinterpret_cast<const ulonglong2 *>(pv[0] + j * 32);
+          const ulonglong2 da = *reinterpret_cast<const ulonglong2 *>(pv[0] + (kInterpChunk + j) * 32);
+          const ulonglong2 vb = *reinterpret_cast<const ulonglong2 *>(pv[3] + j * 32);
+          const ulonglong2 db = *reinterpret_cast<const ulonglong2 *>(pv[3] + (kInterpChunk + j) * 32);
 #pragma unroll
-        for (int k = 0; k < kInterpPx; ++k) {
-          const float4 v = pv[k][j * 32], d = pv[k][(kInterpChunk + j) * 32];
-          px[k] = lerp_px(v, d, xr[k]) | (__float_as_uint(v.w) & keep_lo[k]) |
-                  (__float_as_uint(d.w) & keep_hi[k]);
+          for (int k = 0; k < kInterpPx; ++k) {
+            const bool b = k == 3 || (k > 0 && use_b[k]);
+            px[k] = staged_px(make_ulonglong2(b ? vb.x : va.x, b ? vb.y : va.y),
+                              make_ulonglong2(b ? db.x : da.x, b ? db.y : da.y), xr[k], keep_lo[k],
+                              keep_hi[k]);
+          }
+        } else {
+#pragma unroll
+          for (int k = 0; k < kInterpPx; ++k)
+            px[k] = staged_px(*reinterpret_cast<const ulonglong2 *>(pv[k] + j * 32),
+                              *reinterpret_cast<const ulonglong2 *>(pv[k] + (kInterpChunk + j) * 32),
+                              xr[k], keep_lo[k], keep_hi[k]);
         }
         if (r0 + j < nrows) __stcs(orow4, make_uint4(px[0], px[1], px[2], px[3]));
         orow4 += W / 4;

@@ -340,6 +340,46 @@ class Projections:
             view_y))
 
 
+class VideoFrameConverter:
+    """The colour conversion of VideoEncoder::EncodeFrame (video_encoder.cc:380-398) on the device:
+    RGB0 -> YUV420P planes (the reference's sw_format) or an NV12 surface, libswscale's C arithmetic."""
+
+    def __init__(self, cl_manager: OpenCLManager | None = None):
+        self.m = cl_manager
+
+    def _need(self):
+        if self.m is None or not self.m.ctx:
+            raise FovError("Not initialized with OpenCL")
+
+    def RGB0ToYUV420P(self, y, y_linesize, u, u_linesize, v, v_linesize, source_buffer,
+                      source_linesize, width, height):
+        self._need()
+        self.m._check(self.m.lib.fov_rgb0_to_yuv420p(
+            self.m.ctx, _ptr(y), y_linesize, _ptr(u), u_linesize, _ptr(v), v_linesize,
+            _ptr(source_buffer), source_linesize, width, height))
+
+    def RGB0ToNV12(self, y, y_linesize, uv, uv_linesize, source_buffer, source_linesize, width,
+                   height):
+        self._need()
+        self.m._check(self.m.lib.fov_rgb0_to_nv12(
+            self.m.ctx, _ptr(y), y_linesize, _ptr(uv), uv_linesize, _ptr(source_buffer),
+            source_linesize, width, height))
+
+    def RGB0ToYUV420PFrames(self, n, y, y_stride, y_linesize, u, v, chroma_stride, chroma_linesize,
+                            source_buffer, source_stride, source_linesize, width, height):
+        self._need()
+        self.m._check(self.m.lib.fov_rgb0_to_yuv420p_batched(
+            self.m.ctx, n, _ptr(y), y_stride, y_linesize, _ptr(u), _ptr(v), chroma_stride,
+            chroma_linesize, _ptr(source_buffer), source_stride, source_linesize, width, height))
+
+    def RGB0ToNV12Frames(self, n, y, y_stride, y_linesize, uv, uv_stride, uv_linesize,
+                         source_buffer, source_stride, source_linesize, width, height):
+        self._need()
+        self.m._check(self.m.lib.fov_rgb0_to_nv12_batched(
+            self.m.ctx, n, _ptr(y), y_stride, y_linesize, _ptr(uv), uv_stride, uv_linesize,
+            _ptr(source_buffer), source_stride, source_linesize, width, height))
+
+
 def reduced_dim(full_dim: int) -> int:
     """16*ceil(dim/1.8/16), run_satlogrectilinear.cc:113-114."""
     return int(_capi.load().fov_reduced_dim(int(full_dim)))

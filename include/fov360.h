@@ -210,6 +210,34 @@ int fov_sat_interpolate_gnomonic(fov_ctx *ctx, uint8_t *out, int out_width, int 
                                  int full_width, int full_height, float gaze_x, float gaze_y,
                                  float view_x, float view_y);
 
+/* ---- VideoEncoder colour conversion (video_encoder.cc:380-398) ------- */
+
+/* The reference hands the foveated RGB0 buffer to NVENC through
+ * sws_getContext(w, h, RGB0, w, h, YUV420P, SWS_BILINEAR) + sws_scale on the host and
+ * av_hwframe_transfer_data (video_encoder.cc:389-398).  These entry points produce the same planes
+ * on the device - bit-exact with libswscale's C arithmetic (SWS_BITEXACT; the x86 SIMD path the
+ * plain call takes differs by at most 1 LSB in chroma) - straight into the surface the hardware
+ * encoder reads: y/u/v + linesizes are AVFrame::data[0..2] / linesize[0..2] of the AV_PIX_FMT_CUDA
+ * frame (sw_format YUV420P, video_encoder.cc:549).  BT.601 limited range, chroma = horizontal
+ * pair sums through the matrix, then the vertical taps 1/8 3/8 3/8 1/8 on rows 2j-1..2j+2.
+ * width and height must be even and height >= 8 (libswscale builds other filters below that):
+ * FOV_ERR_UNSUPPORTED otherwise.  src: RGB0 u8[height][src_linesize]. */
+int fov_rgb0_to_yuv420p(fov_ctx *ctx, uint8_t *y, int y_linesize, uint8_t *u, int u_linesize,
+                        uint8_t *v, int v_linesize, const uint8_t *src, int src_linesize,
+                        int width, int height);
+/* Same samples in NVENC's native NV12 layout: uv = u8[height/2][uv_linesize], U and V interleaved. */
+int fov_rgb0_to_nv12(fov_ctx *ctx, uint8_t *y, int y_linesize, uint8_t *uv, int uv_linesize,
+                     const uint8_t *src, int src_linesize, int width, int height);
+/* n frames in one launch (the serving configuration: one reduced buffer per stream); frame f of a
+ * plane lives at base + f*stride (BYTES); u and v share chroma_stride and chroma_linesize. */
+int fov_rgb0_to_yuv420p_batched(fov_ctx *ctx, int n, uint8_t *y, size_t y_stride, int y_linesize,
+                                uint8_t *u, uint8_t *v, size_t chroma_stride, int chroma_linesize,
+                                const uint8_t *src, size_t src_stride, int src_linesize, int width,
+                                int height);
+int fov_rgb0_to_nv12_batched(fov_ctx *ctx, int n, uint8_t *y, size_t y_stride, int y_linesize,
+                             uint8_t *uv, size_t uv_stride, int uv_linesize, const uint8_t *src,
+                             size_t src_stride, int src_linesize, int width, int height);
+
 /* ---- parameters.h semantics ------------------------------------------------------------ */
 
 /* REDUCED_BUFFER_WIDTH/HEIGHT (parameters.h:8-9) for 1920x1080, and the runner's general rule

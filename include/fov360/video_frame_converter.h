@@ -1,0 +1,54 @@
+// Device-side replacement for the colour conversion inside the reference's
+// VideoEncoder::EncodeFrame (src/video_encoder.cc:380-398): sws_getContext(RGB0 -> YUV420P,
+// SWS_BILINEAR) + sws_scale on the host, then av_hwframe_transfer_data.  The reduced buffer is
+// already on the device, so the planes are written straight into the AV_PIX_FMT_CUDA frame's
+// data[0..2] (sw_format YUV420P, video_encoder.cc:549) - or into an NV12 surface - with
+// libswscale's exact C arithmetic.  A maintainer replaces video_encoder.cc:380-398 by one call:
+//
+//   converter.RGB0ToYUV420P(hw_frame->data, hw_frame->linesize, cl_out_buffer(), 4 * width,
+//                           width, height);
+//
+// Errors follow the reference's convention: print to std::cerr and return.
+#pragma once
+#include <iostream>
+
+#include "opencl_manager.h"
+
+class VideoFrameConverter {
+ public:
+  VideoFrameConverter() = default;
+  explicit VideoFrameConverter(OpenCLManager *cl_manager) : cl_manager_(cl_manager) {}
+
+  // data / linesize: AVFrame::data[0..2] and AVFrame::linesize[0..2] of a device frame.
+  void RGB0ToYUV420P(uint8_t *const data[3], const int linesize[3], cl_mem cl_source_buffer,
+                     int source_linesize, int width, int height) {
+    if (!Ready()) return;
+    Report("RGB0ToYUV420P",
+           fov_rgb0_to_yuv420p(cl_manager_->handle(), data[0], linesize[0], data[1], linesize[1],
+                               data[2], linesize[2],
+                               static_cast<const uint8_t *>(cl_source_buffer), source_linesize,
+                               width, height));
+  }
+
+  // data / linesize: the Y plane and the interleaved UV plane of an NV12 surface.
+  void RGB0ToNV12(uint8_t *const data[2], const int linesize[2], cl_mem cl_source_buffer,
+                  int source_linesize, int width, int height) {
+    if (!Ready()) return;
+    Report("RGB0ToNV12",
+           fov_rgb0_to_nv12(cl_manager_->handle(), data[0], linesize[0], data[1], linesize[1],
+                            static_cast<const uint8_t *>(cl_source_buffer), source_linesize, width,
+                            height));
+  }
+
+ private:
+  bool Ready() const {
+    if (cl_manager_ && cl_manager_->handle()) return true;
+    std::cerr << "Not initialized with OpenCL" << std::endl;
+    return false;
+  }
+  void Report(const char *what, int rc) const {
+    if (rc != FOV_OK)
+      std::cerr << what << " failed: " << fov_last_error_string(cl_manager_->handle()) << std::endl;
+  }
+  OpenCLManager *cl_manager_ = nullptr;
+};

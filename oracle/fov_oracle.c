@@ -536,6 +536,78 @@ void orc_gnomonic(uint8_t *out, int tw, int th, const uint8_t *src, int W, int H
   }
 }
 
+/* ------------------------------------------------------------------------------------------
+ * VideoEncoder::EncodeFrame colour conversion (video_encoder.cc:380-398):
+ * sws_getContext(w, h, RGB0, w, h, YUV420P, SWS_BILINEAR) + sws_scale.  The arithmetic is
+ * libswscale's (a third-party dependency; its FFmpeg 4.2 sources are vendored under
+ * /root/reference/include/FFmpeg42/libswscale, cited below as sws/<file>:<line>); restated here in
+ * its C (SWS_BITEXACT) form.  Pinned by tests/golden/swscale_*.npz, generated by the REAL
+ * libswscale binary present in the build container (tests/golden/make_golden_swscale.py).
+ *
+ *  - coefficients: ITU-R BT.601 limited range, 15-bit fixed point, (int)(k * 2^15 + 0.5)
+ *    (sws/utils.c:807-816);
+ *  - luma: a 14-bit value per pixel with rounding term (32 << 14) + 256 and shift 9
+ *    (sws/input.c:252-275 with the bgr32 wrapper's shifts, :378), widened to 15 bits by the
+ *    identity horizontal filter (x 2^14 >> 13, saturating at 2^15 - 1, sws/swscale.c:96-122) and
+ *    narrowed with the constant "dither" 64: (v + 64) >> 7 (sws/output.c:395-403,
+ *    sws/swscale.c:351-352);
+ *  - chroma: horizontal pairs are summed BEFORE the matrix (the "_half" input readers,
+ *    sws/input.c:305-345; chosen because the output is horizontally subsampled and
+ *    SWS_FULL_CHR_H_INP is not set, sws/utils.c:1391-1405): rounding term (256 << 15) + 512,
+ *    shift 10; widened to 15 bits like luma; vertically the bilinear 2:1 filter has the four
+ *    12-bit taps 512, 1536, 1536, 512 on source rows 2j-1 .. 2j+2, rows outside the frame
+ *    replicate the edge row (sws/utils.c:403-418, :494 and its border fix-up), accumulated on
+ *    64 << 12 and shifted by 19 (sws/output.c:380-393).
+ * Preconditions (outside them libswscale builds other filters): W and H even, H >= 8. */
+enum {
+  kRY = 8414, kGY = 16519, kBY = 3208,     /* (int)(0.299|0.587|0.114 * 219/255 * 2^15 + 0.5) */
+  kRU = -4865, kGU = -9528, kBU = 14392,   /* -(int)(0.169..), -(int)(0.331..), (int)(0.500 * 224/255 ..) */
+  kRV = 14392, kGV = -12061, kBV = -2332
+};
+
+static inline uint8_t clip_u8(int v) { return (uint8_t)(v < 0 ? 0 : (v > 255 ? 255 : v)); }
+static inline int widen15(int v14) { return imin(v14 * 2, 32767); }
+
+/* 15-bit chroma of the horizontal pixel pair i of one source row */
+static inline void chroma15_pair(const uint8_t *row, int i, int *u15, int *v15) {
+  const uint8_t *p = row + (size_t)8 * i;
+  const int r = p[0] + p[4], g = p[1] + p[5], b = p[2] + p[6];
+  const int rnd = (256 << 15) + 512;
+  *u15 = widen15((kRU * r + kGU * g + kBU * b + rnd) >> 10);
+  *v15 = widen15((kRV * r + kGV * g + kBV * b + rnd) >> 10);
+}
+
+int orc_rgb0_to_yuv420p(uint8_t *y, int y_linesize, uint8_t *u, int u_linesize, uint8_t *v,
+                        int v_linesize, const uint8_t *src, int src_linesize, int W, int H) {
+  if (W < 2 || H < 8 || (W & 1) || (H & 1)) return -2;
+#pragma omp parallel for num_threads(NT) schedule(static)
+  for (int yy = 0; yy < H; ++yy) {
+    const uint8_t *row = src + (size_t)yy * src_linesize;
+    for (int x = 0; x < W; ++x) {
+      const uint8_t *p = row + (size_t)4 * x;
+      const int y14 = (kRY * p[0] + kGY * p[1] + kBY * p[2] + (32 << 14) + 256) >> 9;
+      y[(size_t)yy * y_linesize + x] = clip_u8((widen15(y14) + 64) >> 7);
+    }
+  }
+#pragma omp parallel for num_threads(NT) schedule(static)
+  for (int j = 0; j < H / 2; ++j) {
+    static const int tap[4] = {512, 1536, 1536, 512};
+    for (int i = 0; i < W / 2; ++i) {
+      int su = 64 << 12, sv = 64 << 12;
+      for (int k = 0; k < 4; ++k) {
+        const int yy = iclamp(2 * j - 1 + k, 0, H - 1);
+        int cu, cv;
+        chroma15_pair(src + (size_t)yy * src_linesize, i, &cu, &cv);
+        su += tap[k] * cu;
+        sv += tap[k] * cv;
+      }
+      u[(size_t)j * u_linesize + i] = clip_u8(su >> 19);
+      v[(size_t)j * v_linesize + i] = clip_u8(sv >> 19);
+    }
+  }
+  return 0;
+}
+
 uint64_t orc_fnv1a64(const uint8_t *p, size_t n) {
   uint64_t h = 0xcbf29ce484222325ull;
   for (size_t i = 0; i < n; ++i) {

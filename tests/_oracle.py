@@ -85,6 +85,8 @@ class Oracle:
         self._img_logpolar_blur = sig("img_logpolar_blur", _u8p, _i, _i, _i, _u8p)
         self._gnomonic = sig("gnomonic", _u8p, _i, _i, _u8p, _i, _i, _f, _f)
         if kind == "port":
+            self._rgb0_to_yuv420p = sig("rgb0_to_yuv420p", _u8p, _i, _u8p, _i, _u8p, _i, _u8p, _i,
+                                        _i, _i, res=_i)
             self._sat_grid_edges = sig("sat_grid_edges", _i16p, _i16p, _i, _i, _i, _i)
             self._fnv = sig("fnv1a64", C.c_void_p, C.c_size_t, res=C.c_uint64)
             self._fill = sig("fill_frame_lcg", _u8p, C.c_size_t, C.c_uint32)
@@ -188,6 +190,19 @@ class Oracle:
             out = np.zeros((oh, ow, 4), np.uint8)
         self._img_logpolar_blur(out, ow, oh, ow * 4, np.ascontiguousarray(reduced))
         return out
+
+    # -- colour conversion (port only: the pin is libswscale itself, tests/golden/swscale_*) ----
+    def rgb0_to_yuv420p(self, rgb0: np.ndarray):
+        """u8[H][W][4] -> (Y u8[H][W], U u8[H/2][W/2], V u8[H/2][W/2]); video_encoder.cc:380-398."""
+        H, W, _ = rgb0.shape
+        y = np.zeros((H, W), np.uint8)
+        u = np.zeros((H // 2, W // 2), np.uint8)
+        v = np.zeros((H // 2, W // 2), np.uint8)
+        rc = self._rgb0_to_yuv420p(y, W, u, W // 2, v, W // 2, np.ascontiguousarray(rgb0), W * 4,
+                                   W, H)
+        if rc != 0:
+            raise ValueError("rgb0_to_yuv420p: unsupported size %dx%d" % (W, H))
+        return y, u, v
 
     # -- helpers (port only) ------------------------------------------------------
     def sat_grid_edges(self, ow, oh, W, H):

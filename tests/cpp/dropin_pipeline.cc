@@ -15,6 +15,7 @@
 #include "fov360/projections.h"
 #include "fov360/sat_decoder.h"
 #include "fov360/sat_encoder.h"
+#include "fov360/video_frame_converter.h"
 
 struct CodecCtxStub {  // stands in for AVCodecContext: only width/height are read
   int width, height;
@@ -51,6 +52,7 @@ int main(int argc, char **argv) {
   SATDecoder sat_decoder(&cl_manager);
   ImageSampler image_sampler(&cl_manager);
   Projections projections(&cl_manager);
+  VideoFrameConverter converter(&cl_manager);
   CodecCtxStub codec_ctx{W, H};
 
   cl::Buffer cl_source_buffer(cl_manager.context, CL_MEM_READ_WRITE, (size_t)linesize * H);
@@ -80,6 +82,17 @@ int main(int argc, char **argv) {
   image_sampler.SampleFrameLogPolarGPU(cl_lp_buffer(), ow, oh, out_linesize, cl_source_buffer(), W,
                                        H, linesize, cx, cy);
 
+  // server side, video_encoder.cc:380-398: the reduced buffer becomes the encoder's YUV420P
+  // surface on the device (planes of one allocation, like a hardware frame)
+  cl::Buffer cl_yuv_buffer(cl_manager.context, CL_MEM_READ_WRITE, (size_t)ow * oh * 3 / 2);
+  uint8_t *yuv_base = static_cast<uint8_t *>(cl_yuv_buffer());
+  uint8_t *const yuv_data[3] = {yuv_base, yuv_base + (size_t)ow * oh,
+                                yuv_base + (size_t)ow * oh * 5 / 4};
+  const int yuv_linesize[3] = {ow, ow / 2, ow / 2};
+  converter.RGB0ToYUV420P(yuv_data, yuv_linesize, cl_out_buffer(), out_linesize, ow, oh);
+  std::vector<uint8_t> yuv((size_t)ow * oh * 3 / 2);
+  cl::copy(cl_manager.command_queue, cl_yuv_buffer, yuv.begin(), yuv.end());
+
   // client side, projections.cc:51-86: viewport out of the un-warped frame, and the fused form
   projections.GnomonicProjection(cl_view_buffer(), vw, vh, 4 * vw, cl_full_buffer(), W, H, linesize,
                                  cx, cy);
@@ -96,11 +109,12 @@ int main(int argc, char **argv) {
 
   printf("{\"W\": %d, \"H\": %d, \"ow\": %d, \"oh\": %d, \"sat\": \"%016llx\", "
          "\"reduced_zero\": \"%016llx\", \"interp\": \"%016llx\", \"logpolar\": \"%016llx\", "
-         "\"view_equal\": %d, \"launches\": %llu}\n",
+         "\"view_equal\": %d, \"yuv420p\": \"%016llx\", \"launches\": %llu}\n",
          W, H, ow, oh, (unsigned long long)fnv1a64(sat.data(), sat.size() * 4),
          (unsigned long long)fnv1a64(reduced.data(), reduced.size()),
          (unsigned long long)fnv1a64(full.data(), full.size()),
          (unsigned long long)fnv1a64(logpolar.data(), logpolar.size()), (int)(view == view2),
+         (unsigned long long)fnv1a64(yuv.data(), yuv.size()),
          (unsigned long long)fov_ctx_launch_count(cl_manager.handle()));
   return 0;
 }

@@ -29,7 +29,7 @@ def test_dropin_headers_compile_and_link(fov):
 
 
 @pytest.mark.gpu
-def test_dropin_call_sequence_matches_golden(fov, golden):
+def test_dropin_call_sequence_matches_golden(fov, golden, oracle):
     exe = build_exe(fov)
     c = golden["sat"][0]
     g = c["gaze"][1]
@@ -43,4 +43,13 @@ def test_dropin_call_sequence_matches_golden(fov, golden):
     lp = [x for x in golden["logpolar"][0]["gaze"] if (x["cx"], x["cy"]) == (g["cx"], g["cy"])][0]
     assert got["logpolar"] == lp["logpolar"]
     assert got["view_equal"] == 1  # Projections: fused viewport == interpolate + gnomonic
-    assert got["launches"] >= 6
+    # VideoFrameConverter: the encoder surface equals libswscale's conversion of the reduced buffer
+    import numpy as np
+
+    import _oracle as O
+    red = oracle.sat_sample_rect(oracle.sat_encode(O.lcg_frame(c["W"], c["H"], c["seed"])),
+                                 c["ow"], c["oh"], g["cx"], g["cy"])
+    assert O.fnv1a64(red) == g["reduced_zero"]
+    y, u, v = oracle.rgb0_to_yuv420p(red)
+    assert got["yuv420p"] == O.fnv1a64(np.concatenate([y.ravel(), u.ravel(), v.ravel()]))
+    assert got["launches"] >= 7

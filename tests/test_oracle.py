@@ -170,3 +170,52 @@ def test_wraparound_all_white(oracle):
     red = oracle.sat_sample_rect(sat, ow, oh, 0.9, 0.9, out=np.full((oh, ow, 4), 0xAB, np.uint8))
     written = (red[..., :3] != 0xAB).any(axis=2)
     assert written.any() and (red[written][:, :3] == 255).all()
+
+
+# ---- RGB0 -> YUV420P (video_encoder.cc:380-398): pinned to the real libswscale ---------------
+
+def _golden_path(name):
+    import os
+    return os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", name)
+
+
+def test_yuv420p_small_matches_libswscale(oracle):
+    g = np.load(_golden_path("swscale_small.npz"))
+    y, u, v = oracle.rgb0_to_yuv420p(g["rgb0"])
+    # bit-exact against libswscale's C arithmetic (SWS_BITEXACT) ...
+    assert np.array_equal(y, g["y"]) and np.array_equal(u, g["u"]) and np.array_equal(v, g["v"])
+    # ... and within 1 LSB of what the reference's plain SWS_BILINEAR call returns on x86 (the SIMD
+    # vertical scaler rounds differently); luma is identical
+    assert np.array_equal(y, g["y_simd"])
+    assert np.abs(u.astype(int) - g["u_simd"]).max() <= 1
+    assert np.abs(v.astype(int) - g["v_simd"]).max() <= 1
+
+
+def test_yuv420p_hashes_match_libswscale(oracle):
+    import json
+    with open(_golden_path("swscale.json")) as fh:
+        cases = json.load(fh)["cases"]
+    for c in cases:
+        if c["W"] * c["H"] > 2144 * 1072:
+            continue  # the 8K reduced buffer is covered on the GPU side
+        frame = O.lcg_frame(c["W"], c["H"], c["seed"])
+        assert O.fnv1a64(frame) == c["frame"]
+        y, u, v = oracle.rgb0_to_yuv420p(frame)
+        assert (O.fnv1a64(y), O.fnv1a64(u), O.fnv1a64(v)) == (c["y"], c["u"], c["v"]), c
+
+
+def test_yuv420p_known_colours_and_size_contract(oracle):
+    def flat(r, g, b, W=16, H=8):
+        img = np.zeros((H, W, 4), np.uint8)
+        img[..., 0], img[..., 1], img[..., 2] = r, g, b
+        return img
+    # BT.601 limited range: black (16,128,128), white (235,128,128), primaries
+    for rgb, yuv in [((0, 0, 0), (16, 128, 128)), ((255, 255, 255), (235, 128, 128)),
+                     ((255, 0, 0), (81, 90, 240)), ((0, 255, 0), (145, 54, 34)),
+                     ((0, 0, 255), (41, 240, 110))]:
+        y, u, v = oracle.rgb0_to_yuv420p(flat(*rgb))
+        assert (int(y[3, 5]), int(u[1, 2]), int(v[1, 2])) == yuv
+        assert len(np.unique(y)) == len(np.unique(u)) == len(np.unique(v)) == 1
+    for W, H in [(15, 8), (16, 9), (16, 6), (0, 8)]:  # odd sizes / too few rows: other filters
+        with pytest.raises(ValueError):
+            oracle.rgb0_to_yuv420p(np.zeros((H, W, 4), np.uint8))

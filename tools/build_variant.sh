@@ -6,7 +6,7 @@ cd "$(dirname "$0")/.."
 name=$1; shift
 mkdir -p tools/variants/obj_$name
 C=foveated-360-video_b200/csrc
-for f in capi sat_encode sat_onepass sat_decode image_sampler projections; do
+for f in capi sat_encode sat_onepass sat_decode image_sampler projections color_convert; do
   nvcc -O3 -std=c++17 -lineinfo -gencode arch=compute_100a,code=sm_100a -Xcompiler -fPIC,-ffp-contract=off,-fno-fast-math \
        -I include -I $C $@ -c $C/$f.cu -o tools/variants/obj_$name/$f.o &
 done
