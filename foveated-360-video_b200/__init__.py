@@ -12,6 +12,7 @@ from .host import (  # noqa: F401
     DeviceBuffer,
     FoveateFramesGPU,
     FovError,
+    GazeViewPoints,
     ImageSampler,
     OpenCLManager,
     Projections,

@@ -65,6 +65,11 @@ PROTOTYPES = {
     "fov_rgb0_to_yuv420p_batched": (_i, [_vp, _i, _vp, _sz, _i, _vp, _vp, _sz, _i, _vp, _sz, _i,
                                          _i, _i]),
     "fov_rgb0_to_nv12_batched": (_i, [_vp, _i, _vp, _sz, _i, _vp, _sz, _i, _vp, _sz, _i, _i, _i]),
+    "fov_yuv420p_to_rgb0": (_i, [_vp, _vp, _i, _vp, _i, _vp, _i, _vp, _i, _i, _i]),
+    "fov_nv12_to_rgb0": (_i, [_vp, _vp, _i, _vp, _i, _vp, _i, _i, _i]),
+    "fov_yuv420p_to_rgb0_batched": (_i, [_vp, _i, _vp, _sz, _i, _vp, _sz, _i, _vp, _vp, _sz, _i,
+                                         _i, _i]),
+    "fov_nv12_to_rgb0_batched": (_i, [_vp, _i, _vp, _sz, _i, _vp, _sz, _i, _vp, _sz, _i, _i, _i]),
     "fov_reduced_dim": (_i, [_i]),
 }
 

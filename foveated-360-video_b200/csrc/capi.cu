@@ -794,6 +794,63 @@ int fov_rgb0_to_nv12_batched(fov_ctx *ctx, int n, uint8_t *y, size_t y_stride, i
                      height);
 }
 
+// ---- VideoDecoder colour conversion ------------------------------------------------------------
+
+namespace {
+int rgb_convert(fov_ctx *ctx, const char *who, bool nv12, int n, uint8_t *dst, size_t dst_stride,
+                int dst_ls, const uint8_t *y, size_t y_stride, int y_ls, const uint8_t *u, int u_ls,
+                const uint8_t *v, int v_ls, size_t c_stride, int W, int H) {
+  FOV_REQUIRE_CTX(ctx);
+  const int cw = nv12 ? W : W / 2;  // bytes per chroma row
+  if (!dst || !y || !u || (!nv12 && !v) || n < 1 || W <= 0 || H <= 0 || y_ls < W || u_ls < cw ||
+      (!nv12 && v_ls < cw) || dst_ls < 4 * W || (dst_ls & 3) || ((uintptr_t)dst & 3) ||
+      (dst_stride & 3))
+    return fail(ctx, FOV_ERR_INVALID, std::string(who) + ": invalid arguments");
+  if ((W & 1) || (H & 1))
+    return fail(ctx, FOV_ERR_UNSUPPORTED, std::string(who) + ": width and height must be even");
+  DeviceGuard g(ctx);
+  for (int f0 = 0; f0 < n; f0 += 65535) {  // gridDim.z limit
+    const int nf = std::min(n - f0, 65535);
+    FOV_CUDA(ctx,
+             launch_yuv_to_rgb0(ctx->lc(), nv12, nf, dst + (size_t)f0 * dst_stride, dst_stride,
+                                dst_ls, y + (size_t)f0 * y_stride, y_stride, y_ls,
+                                u + (size_t)f0 * c_stride, u_ls,
+                                v ? v + (size_t)f0 * c_stride : nullptr, v_ls, c_stride, W, H),
+             who);
+  }
+  return FOV_OK;
+}
+}  // namespace
+
+int fov_yuv420p_to_rgb0(fov_ctx *ctx, uint8_t *dst, int dst_linesize, const uint8_t *y,
+                        int y_linesize, const uint8_t *u, int u_linesize, const uint8_t *v,
+                        int v_linesize, int width, int height) {
+  return rgb_convert(ctx, "fov_yuv420p_to_rgb0", false, 1, dst, 0, dst_linesize, y, 0, y_linesize,
+                     u, u_linesize, v, v_linesize, 0, width, height);
+}
+
+int fov_nv12_to_rgb0(fov_ctx *ctx, uint8_t *dst, int dst_linesize, const uint8_t *y, int y_linesize,
+                     const uint8_t *uv, int uv_linesize, int width, int height) {
+  return rgb_convert(ctx, "fov_nv12_to_rgb0", true, 1, dst, 0, dst_linesize, y, 0, y_linesize, uv,
+                     uv_linesize, nullptr, 0, 0, width, height);
+}
+
+int fov_yuv420p_to_rgb0_batched(fov_ctx *ctx, int n, uint8_t *dst, size_t dst_stride,
+                                int dst_linesize, const uint8_t *y, size_t y_stride, int y_linesize,
+                                const uint8_t *u, const uint8_t *v, size_t chroma_stride,
+                                int chroma_linesize, int width, int height) {
+  return rgb_convert(ctx, "fov_yuv420p_to_rgb0_batched", false, n, dst, dst_stride, dst_linesize, y,
+                     y_stride, y_linesize, u, chroma_linesize, v, chroma_linesize, chroma_stride,
+                     width, height);
+}
+
+int fov_nv12_to_rgb0_batched(fov_ctx *ctx, int n, uint8_t *dst, size_t dst_stride, int dst_linesize,
+                             const uint8_t *y, size_t y_stride, int y_linesize, const uint8_t *uv,
+                             size_t uv_stride, int uv_linesize, int width, int height) {
+  return rgb_convert(ctx, "fov_nv12_to_rgb0_batched", true, n, dst, dst_stride, dst_linesize, y,
+                     y_stride, y_linesize, uv, uv_linesize, nullptr, 0, uv_stride, width, height);
+}
+
 int fov_reduced_dim(int full_dim) {
   // 16 * ceil(dim / 1.8 / 16), run_satlogrectilinear.cc:113-114
   return 16 * (int)std::ceil(full_dim / 1.8 / 16);

@@ -1,4 +1,6 @@
-// RGB0 -> YUV420P / NV12 on the device.
+// Colour conversions either side of the foveation path, on the device.
+//
+// RGB0 -> YUV420P / NV12:
 //
 // Replaces the colour conversion inside VideoEncoder::EncodeFrame (video_encoder.cc:380-398):
 // the reference copies the foveated RGB0 buffer to the host, runs
@@ -133,7 +135,95 @@ __global__ void __launch_bounds__(256) rgb0_to_yuv_kernel(const YuvArgs a) {
   }
 }
 
+// ---- YUV420P / NV12 -> RGB0 --------------------------------------------
+//
+// Replaces the sws_scale inside VideoDecoder::GetFrame (video_decoder.cc:165-170, :222) so that a
+// frame decoded on the device (NVDEC hands out NV12 surfaces) becomes the RGB0 frame
+// EncodeFrameGPU reads without a host round trip.  libswscale converts same-size YUV420P to packed
+// RGB with its yuv2rgb converter: chroma is replicated over each 2x2 block and the arithmetic is
+// 16-bit fixed point (x86/yuv2rgb_template.c:95-98, coefficients yuv2rgb.c:830-837):
+//   Y' = (((Y << 3) - 128) * 9539) >> 16,  U' = (U << 3) - 1024,  V' = (V << 3) - 1024
+//   R = clip8(Y' + (V' * 13075 >> 16)),  G = clip8(Y' + (U' * -3209 >> 16) + (V' * -6660 >> 16)),
+//   B = clip8(Y' + (U' * 16525 >> 16)),  4th byte = 255.
+struct RgbArgs {
+  uint8_t *dst;
+  const uint8_t *y, *u, *v;  // v unused for NV12 (u = the interleaved plane)
+  size_t dst_stride, y_stride, c_stride;
+  int dst_ls, y_ls, c_ls, v_ls;
+  int W, H;
+};
+
+__device__ __forceinline__ uint32_t yuv_px(int Y, int rv, int guv, int bu) {
+  const int yt = (((Y << 3) - 128) * 9539) >> 16;
+  return (uint32_t)clip8(yt + rv) | ((uint32_t)clip8(yt + guv) << 8) |
+         ((uint32_t)clip8(yt + bu) << 16) | 0xff000000u;
+}
+
+// One thread: 4 consecutive pixels x 2 rows (two chroma samples).
+template <bool kNV12>
+__global__ void __launch_bounds__(256) yuv_to_rgb0_kernel(const RgbArgs a) {
+  const int x0 = (blockIdx.x * 32 + threadIdx.x) * 4;
+  const int j = blockIdx.y * 8 + threadIdx.y;  // chroma row
+  const int W = a.W, H = a.H;
+  if (x0 >= W || 2 * j >= H) return;
+  const int f = blockIdx.z;
+  const bool full = x0 + 4 <= W;  // false only for the last thread of a row when W % 4 == 2
+  int U[2], V[2];
+  if (kNV12) {
+    const uint8_t *c = a.u + (size_t)f * a.c_stride + (size_t)j * a.c_ls + x0;
+    U[0] = c[0], V[0] = c[1];
+    U[1] = full ? c[2] : 0, V[1] = full ? c[3] : 0;
+  } else {
+    const uint8_t *up = a.u + (size_t)f * a.c_stride + (size_t)j * a.c_ls + x0 / 2;
+    const uint8_t *vp = a.v + (size_t)f * a.c_stride + (size_t)j * a.v_ls + x0 / 2;
+    U[0] = up[0], V[0] = vp[0];
+    U[1] = full ? up[1] : 0, V[1] = full ? vp[1] : 0;
+  }
+  int rv[2], guv[2], bu[2];
+#pragma unroll
+  for (int p = 0; p < 2; ++p) {
+    const int us = (U[p] << 3) - 1024, vs = (V[p] << 3) - 1024;
+    rv[p] = (vs * 13075) >> 16;
+    guv[p] = ((us * -3209) >> 16) + ((vs * -6660) >> 16);
+    bu[p] = (us * 16525) >> 16;
+  }
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const uint8_t *yrow = a.y + (size_t)f * a.y_stride + (size_t)(2 * j + r) * a.y_ls + x0;
+    uint32_t px[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      px[k] = (k < 2 || full) ? yuv_px(yrow[k], rv[k / 2], guv[k / 2], bu[k / 2]) : 0u;
+    uint8_t *o = a.dst + (size_t)f * a.dst_stride + (size_t)(2 * j + r) * a.dst_ls + (size_t)x0 * 4;
+    if (full && (reinterpret_cast<uintptr_t>(o) & 15) == 0) {
+      *reinterpret_cast<uint4 *>(o) = make_uint4(px[0], px[1], px[2], px[3]);
+    } else {
+      uint32_t *o32 = reinterpret_cast<uint32_t *>(o);
+      o32[0] = px[0], o32[1] = px[1];
+      if (full) o32[2] = px[2], o32[3] = px[3];
+    }
+  }
+}
+
 }  // namespace
+
+cudaError_t launch_yuv_to_rgb0(const LaunchCtx &lc, bool nv12, int n, uint8_t *dst,
+                               size_t dst_stride, int dst_ls, const uint8_t *y, size_t y_stride,
+                               int y_ls, const uint8_t *u, int u_ls, const uint8_t *v, int v_ls,
+                               size_t c_stride, int W, int H) {
+  RgbArgs a;
+  a.dst = dst, a.y = y, a.u = u, a.v = v;
+  a.dst_stride = dst_stride, a.y_stride = y_stride, a.c_stride = c_stride;
+  a.dst_ls = dst_ls, a.y_ls = y_ls, a.c_ls = u_ls, a.v_ls = v_ls;
+  a.W = W, a.H = H;
+  const dim3 grid((W + 127) / 128, (H / 2 + 7) / 8, n), block(32, 8);
+  KernelScope ks(lc, nv12 ? "nv12_to_rgb0" : "yuv420p_to_rgb0");
+  if (nv12)
+    yuv_to_rgb0_kernel<true><<<grid, block, 0, lc.stream>>>(a);
+  else
+    yuv_to_rgb0_kernel<false><<<grid, block, 0, lc.stream>>>(a);
+  return cudaGetLastError();
+}
 
 cudaError_t launch_rgb0_to_yuv(const LaunchCtx &lc, bool nv12, int n, uint8_t *y, size_t y_stride,
                                int y_ls, uint8_t *u, int u_ls, uint8_t *v, int v_ls, size_t c_stride,

@@ -201,5 +201,10 @@ cudaError_t launch_sat_interpolate_gnomonic(const LaunchCtx &lc, uint8_t *out, i
 cudaError_t launch_rgb0_to_yuv(const LaunchCtx &lc, bool nv12, int n, uint8_t *y, size_t y_stride,
                                int y_ls, uint8_t *u, int u_ls, uint8_t *v, int v_ls, size_t c_stride,
                                const uint8_t *src, size_t src_stride, int src_ls, int W, int H);
+// YUV420P / NV12 -> RGB0 (color_convert.cu).  nv12: `u` is the interleaved plane, `v` unused.
+cudaError_t launch_yuv_to_rgb0(const LaunchCtx &lc, bool nv12, int n, uint8_t *dst,
+                               size_t dst_stride, int dst_ls, const uint8_t *y, size_t y_stride,
+                               int y_ls, const uint8_t *u, int u_ls, const uint8_t *v, int v_ls,
+                               size_t c_stride, int W, int H);
 
 }  // namespace fov

@@ -341,8 +341,9 @@ class Projections:
 
 
 class VideoFrameConverter:
-    """The colour conversion of VideoEncoder::EncodeFrame (video_encoder.cc:380-398) on the device:
-    RGB0 -> YUV420P planes (the reference's sw_format) or an NV12 surface, libswscale's C arithmetic."""
+    """The swscale steps either side of the foveation path, on the device: RGB0 -> YUV420P / NV12
+    of VideoEncoder::EncodeFrame (video_encoder.cc:380-398) and YUV420P / NV12 -> RGB0 of
+    VideoDecoder::GetFrame (video_decoder.cc:165-170, :222), with libswscale's arithmetic."""
 
     def __init__(self, cl_manager: OpenCLManager | None = None):
         self.m = cl_manager
@@ -365,6 +366,35 @@ class VideoFrameConverter:
             self.m.ctx, _ptr(y), y_linesize, _ptr(uv), uv_linesize, _ptr(source_buffer),
             source_linesize, width, height))
 
+    # -- decoder side: video_decoder.cc:165-170, :222 ----------------------------------------
+    def YUV420PToRGB0(self, target_buffer, target_linesize, y, y_linesize, u, u_linesize, v,
+                      v_linesize, width, height):
+        self._need()
+        self.m._check(self.m.lib.fov_yuv420p_to_rgb0(
+            self.m.ctx, _ptr(target_buffer), target_linesize, _ptr(y), y_linesize, _ptr(u),
+            u_linesize, _ptr(v), v_linesize, width, height))
+
+    def NV12ToRGB0(self, target_buffer, target_linesize, y, y_linesize, uv, uv_linesize, width,
+                   height):
+        self._need()
+        self.m._check(self.m.lib.fov_nv12_to_rgb0(
+            self.m.ctx, _ptr(target_buffer), target_linesize, _ptr(y), y_linesize, _ptr(uv),
+            uv_linesize, width, height))
+
+    def YUV420PToRGB0Frames(self, n, target_buffer, target_stride, target_linesize, y, y_stride,
+                            y_linesize, u, v, chroma_stride, chroma_linesize, width, height):
+        self._need()
+        self.m._check(self.m.lib.fov_yuv420p_to_rgb0_batched(
+            self.m.ctx, n, _ptr(target_buffer), target_stride, target_linesize, _ptr(y), y_stride,
+            y_linesize, _ptr(u), _ptr(v), chroma_stride, chroma_linesize, width, height))
+
+    def NV12ToRGB0Frames(self, n, target_buffer, target_stride, target_linesize, y, y_stride,
+                         y_linesize, uv, uv_stride, uv_linesize, width, height):
+        self._need()
+        self.m._check(self.m.lib.fov_nv12_to_rgb0_batched(
+            self.m.ctx, n, _ptr(target_buffer), target_stride, target_linesize, _ptr(y), y_stride,
+            y_linesize, _ptr(uv), uv_stride, uv_linesize, width, height))
+
     def RGB0ToYUV420PFrames(self, n, y, y_stride, y_linesize, u, v, chroma_stride, chroma_linesize,
                             source_buffer, source_stride, source_linesize, width, height):
         self._need()
@@ -378,6 +408,57 @@ class VideoFrameConverter:
         self.m._check(self.m.lib.fov_rgb0_to_nv12_batched(
             self.m.ctx, n, _ptr(y), y_stride, y_linesize, _ptr(uv), uv_stride, uv_linesize,
             _ptr(source_buffer), source_stride, source_linesize, width, height))
+
+
+class GazeViewPoint:
+    """gaze_view_points.h:11-17."""
+    __slots__ = ("frame", "view_point", "gaze_point", "pred_view_point", "pred_gaze_point")
+
+    def __init__(self, frame, view_point, gaze_point):
+        self.frame = frame
+        self.view_point = view_point
+        self.gaze_point = gaze_point
+        self.pred_view_point = view_point
+        self.pred_gaze_point = gaze_point
+
+
+class GazeViewPoints:
+    """gaze_view_points.cc:3-37: one record per line containing
+    ``frame,<n>,forward,<x>,<y>,eye,<x>,<y>``; pred_* = the previous record's measured points."""
+
+    _FLOAT = r"([-+]?\d*\.?\d+(?:[eE][-+]?\d+)?)"
+
+    def __init__(self, file_path: str | None = None):
+        import re
+
+        self.points: list[GazeViewPoint] = []
+        if file_path is None:
+            return
+        rx = re.compile(r"frame,(\d+),forward," + self._FLOAT + "," + self._FLOAT + ",eye," +
+                        self._FLOAT + "," + self._FLOAT, re.ASCII)
+        try:
+            fh = open(file_path, "r", errors="replace")
+        except OSError:
+            import sys
+
+            print("Cannot open file: " + file_path, file=sys.stderr)  # gaze_view_points.cc:35
+            return
+        with fh:
+            for line in fh:
+                m = rx.search(line)
+                if not m:
+                    continue
+                f = [float(np.float32(m.group(k))) for k in range(2, 6)]
+                p = GazeViewPoint(int(m.group(1)), (f[0], f[1]), (f[2], f[3]))
+                if self.points:
+                    p.pred_view_point = self.points[-1].view_point
+                    p.pred_gaze_point = self.points[-1].gaze_point
+                self.points.append(p)
+
+    def gaze_array(self) -> np.ndarray:
+        """float32 [n][2] of gaze_point, the (center_x, center_y) of frame f
+        (run_satlogrectilinear.cc:519-521)."""
+        return np.asarray([p.gaze_point for p in self.points], np.float32).reshape(-1, 2)
 
 
 def reduced_dim(full_dim: int) -> int:

@@ -27,6 +27,27 @@ def owner_of(index: int, world: int) -> int:
     return index % world
 
 
+class SessionPlacement:
+    """Least-loaded placement of client sessions on the GPUs of one box; mirrors
+    include/fov360/session_placement.h (the reference binds every connection to device 0,
+    video_server.cc:62-66).  Without disconnects it is the static rule s -> s % G."""
+
+    def __init__(self, device_count: int):
+        self._load = [0] * max(1, int(device_count))
+
+    def acquire(self) -> int:
+        best = min(range(len(self._load)), key=lambda d: (self._load[d], d))
+        self._load[best] += 1
+        return best
+
+    def release(self, device: int) -> None:
+        if 0 <= device < len(self._load) and self._load[device] > 0:
+            self._load[device] -= 1
+
+    def sessions(self, device: int) -> int:
+        return self._load[device] if 0 <= device < len(self._load) else 0
+
+
 def aggregate_throughput(units_per_rank: Sequence[int], seconds_per_rank: Sequence[float]) -> float:
     """Whole-job units/s: all units divided by the slowest rank's time (never a sum of rates)."""
     return float(sum(units_per_rank)) / max(seconds_per_rank)

@@ -238,6 +238,29 @@ int fov_rgb0_to_nv12_batched(fov_ctx *ctx, int n, uint8_t *y, size_t y_stride, i
                              uint8_t *uv, size_t uv_stride, int uv_linesize, const uint8_t *src,
                              size_t src_stride, int src_linesize, int width, int height);
 
+/* ---- VideoDecoder colour conversion (video_decoder.cc:165-170, :222) --- */
+
+/* The reference turns every decoded frame into RGB0 with
+ * sws_getContext(w, h, YUV420P, w, h, RGB0, SWS_BILINEAR) + sws_scale on the host and uploads it
+ * (video_server.cc:291-299).  These entry points do the conversion on the device, so a frame
+ * decoded there (NVDEC produces NV12) feeds fov_sat_encode directly.  Bit-exact with libswscale's
+ * yuv2rgb converter: chroma replicated over 2x2 blocks, 16-bit fixed-point BT.601 limited-range
+ * matrix, 4th byte written as 255.  width and height must be even (FOV_ERR_UNSUPPORTED otherwise).
+ * dst: RGB0 u8[height][dst_linesize] (4-byte aligned). */
+int fov_yuv420p_to_rgb0(fov_ctx *ctx, uint8_t *dst, int dst_linesize, const uint8_t *y,
+                        int y_linesize, const uint8_t *u, int u_linesize, const uint8_t *v,
+                        int v_linesize, int width, int height);
+int fov_nv12_to_rgb0(fov_ctx *ctx, uint8_t *dst, int dst_linesize, const uint8_t *y, int y_linesize,
+                     const uint8_t *uv, int uv_linesize, int width, int height);
+/* n frames in one launch; frame f of a plane lives at base + f*stride (BYTES). */
+int fov_yuv420p_to_rgb0_batched(fov_ctx *ctx, int n, uint8_t *dst, size_t dst_stride,
+                                int dst_linesize, const uint8_t *y, size_t y_stride, int y_linesize,
+                                const uint8_t *u, const uint8_t *v, size_t chroma_stride,
+                                int chroma_linesize, int width, int height);
+int fov_nv12_to_rgb0_batched(fov_ctx *ctx, int n, uint8_t *dst, size_t dst_stride, int dst_linesize,
+                             const uint8_t *y, size_t y_stride, int y_linesize, const uint8_t *uv,
+                             size_t uv_stride, int uv_linesize, int width, int height);
+
 /* ---- parameters.h semantics ------------------------------------------------------------ */
 
 /* REDUCED_BUFFER_WIDTH/HEIGHT (parameters.h:8-9) for 1920x1080, and the runner's general rule

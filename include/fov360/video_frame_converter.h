@@ -8,6 +8,12 @@
 //   converter.RGB0ToYUV420P(hw_frame->data, hw_frame->linesize, cl_out_buffer(), 4 * width,
 //                           width, height);
 //
+// The other direction replaces the sws_scale of VideoDecoder::GetFrame (src/video_decoder.cc:165-170,
+// :222): a frame decoded on the device (YUV420P planes or an NVDEC NV12 surface) becomes the RGB0
+// frame EncodeFrameGPU reads, without the host round trip of video_server.cc:291-299:
+//
+//   converter.NV12ToRGB0(cl_source_buffer(), 4 * width, nv12_data, nv12_linesize, width, height);
+//
 // Errors follow the reference's convention: print to std::cerr and return.
 #pragma once
 #include <iostream>
@@ -37,6 +43,26 @@ class VideoFrameConverter {
     Report("RGB0ToNV12",
            fov_rgb0_to_nv12(cl_manager_->handle(), data[0], linesize[0], data[1], linesize[1],
                             static_cast<const uint8_t *>(cl_source_buffer), source_linesize, width,
+                            height));
+  }
+
+  // data / linesize: the three planes of a decoded YUV420P frame on the device.
+  void YUV420PToRGB0(cl_mem cl_target_buffer, int target_linesize, const uint8_t *const data[3],
+                     const int linesize[3], int width, int height) {
+    if (!Ready()) return;
+    Report("YUV420PToRGB0",
+           fov_yuv420p_to_rgb0(cl_manager_->handle(), static_cast<uint8_t *>(cl_target_buffer),
+                               target_linesize, data[0], linesize[0], data[1], linesize[1], data[2],
+                               linesize[2], width, height));
+  }
+
+  // data / linesize: the Y plane and the interleaved UV plane of an NV12 surface (NVDEC output).
+  void NV12ToRGB0(cl_mem cl_target_buffer, int target_linesize, const uint8_t *const data[2],
+                  const int linesize[2], int width, int height) {
+    if (!Ready()) return;
+    Report("NV12ToRGB0",
+           fov_nv12_to_rgb0(cl_manager_->handle(), static_cast<uint8_t *>(cl_target_buffer),
+                            target_linesize, data[0], linesize[0], data[1], linesize[1], width,
                             height));
   }
 

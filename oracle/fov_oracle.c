@@ -608,6 +608,42 @@ int orc_rgb0_to_yuv420p(uint8_t *y, int y_linesize, uint8_t *u, int u_linesize, 
   return 0;
 }
 
+/* ------------------------------------------------------------------------------------------
+ * VideoDecoder::GetFrame colour conversion (video_decoder.cc:165-170, :222):
+ * sws_getContext(w, h, YUV420P, w, h, RGB0, SWS_BILINEAR) + sws_scale.  Same size and an 8-bit
+ * packed RGB target select libswscale's dedicated yuv2rgb converter (sws/swscale_unscaled.c), not
+ * the scaler: chroma is NOT interpolated (each U/V sample covers its 2x2 luma block) and the
+ * arithmetic is the 16-bit fixed point of the x86 converter the reference's host runs
+ * (sws/x86/yuv2rgb_template.c:95-98 with the coefficients of sws/yuv2rgb.c:830-837):
+ *     Y' = (((Y << 3) - 128) * 9539) >> 16          (9539 = round16(255/219 * 2^13), signed)
+ *     U' = (U << 3) - 1024,  V' = (V << 3) - 1024
+ *     R = clip8(Y' + ((V' * 13075) >> 16))
+ *     G = clip8(Y' + ((U' * -3209) >> 16) + ((V' * -6660) >> 16))
+ *     B = clip8(Y' + ((U' * 16525) >> 16))           (>> = arithmetic shift: pmulhw)
+ * and the 4th byte of RGB0 is written as 255.  Pinned by tests/golden/swscale_*.npz: the real
+ * libswscale returns exactly this with and without SWS_BITEXACT.  W and H even. */
+int orc_yuv420p_to_rgb0(uint8_t *dst, int dst_linesize, const uint8_t *y, int y_linesize,
+                        const uint8_t *u, int u_linesize, const uint8_t *v, int v_linesize, int W,
+                        int H) {
+  if (W < 2 || H < 2 || (W & 1) || (H & 1)) return -2;
+#pragma omp parallel for num_threads(NT) schedule(static)
+  for (int yy = 0; yy < H; ++yy) {
+    for (int x = 0; x < W; ++x) {
+      const int Y = y[(size_t)yy * y_linesize + x];
+      const int U = u[(size_t)(yy / 2) * u_linesize + x / 2];
+      const int V = v[(size_t)(yy / 2) * v_linesize + x / 2];
+      const int yt = (((Y << 3) - 128) * 9539) >> 16;
+      const int up = (U << 3) - 1024, vp = (V << 3) - 1024;
+      uint8_t *o = dst + (size_t)yy * dst_linesize + (size_t)4 * x;
+      o[0] = clip_u8(yt + ((vp * 13075) >> 16));
+      o[1] = clip_u8(yt + ((up * -3209) >> 16) + ((vp * -6660) >> 16));
+      o[2] = clip_u8(yt + ((up * 16525) >> 16));
+      o[3] = 255;
+    }
+  }
+  return 0;
+}
+
 uint64_t orc_fnv1a64(const uint8_t *p, size_t n) {
   uint64_t h = 0xcbf29ce484222325ull;
   for (size_t i = 0; i < n; ++i) {

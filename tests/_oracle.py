@@ -87,6 +87,8 @@ class Oracle:
         if kind == "port":
             self._rgb0_to_yuv420p = sig("rgb0_to_yuv420p", _u8p, _i, _u8p, _i, _u8p, _i, _u8p, _i,
                                         _i, _i, res=_i)
+            self._yuv420p_to_rgb0 = sig("yuv420p_to_rgb0", _u8p, _i, _u8p, _i, _u8p, _i, _u8p, _i,
+                                        _i, _i, res=_i)
             self._sat_grid_edges = sig("sat_grid_edges", _i16p, _i16p, _i, _i, _i, _i)
             self._fnv = sig("fnv1a64", C.c_void_p, C.c_size_t, res=C.c_uint64)
             self._fill = sig("fill_frame_lcg", _u8p, C.c_size_t, C.c_uint32)
@@ -204,6 +206,17 @@ class Oracle:
             raise ValueError("rgb0_to_yuv420p: unsupported size %dx%d" % (W, H))
         return y, u, v
 
+    def yuv420p_to_rgb0(self, y: np.ndarray, u: np.ndarray, v: np.ndarray) -> np.ndarray:
+        """(Y u8[H][W], U, V u8[H/2][W/2]) -> RGB0 u8[H][W][4]; video_decoder.cc:165-222."""
+        H, W = y.shape
+        out = np.zeros((H, W, 4), np.uint8)
+        rc = self._yuv420p_to_rgb0(out.reshape(H, W * 4), W * 4, np.ascontiguousarray(y), W,
+                                   np.ascontiguousarray(u), W // 2, np.ascontiguousarray(v),
+                                   W // 2, W, H)
+        if rc != 0:
+            raise ValueError("yuv420p_to_rgb0: unsupported size %dx%d" % (W, H))
+        return out
+
     # -- helpers (port only) ------------------------------------------------------
     def sat_grid_edges(self, ow, oh, W, H):
         xe = np.zeros(ow + 1, np.int16)
@@ -232,6 +245,13 @@ def lcg_frame(W: int, H: int, seed: int = 12345) -> np.ndarray:
     buf = np.empty(H * W * 4, np.uint8)
     port()._fill(buf, buf.size, seed & 0xFFFFFFFF)
     return buf.reshape(H, W, 4)
+
+
+def lcg_planes(W: int, H: int, seed: int):
+    """Y/U/V planes cut from one LCG frame (as tests/golden/make_golden_swscale.py does)."""
+    f = lcg_frame(W, H, seed)
+    return (np.ascontiguousarray(f[..., 0]), np.ascontiguousarray(f[0::2, 0::2, 1]),
+            np.ascontiguousarray(f[0::2, 0::2, 2]))
 
 
 def smooth_frame(W: int, H: int, seed: int = 7) -> np.ndarray:

@@ -154,3 +154,101 @@ def test_foveated_stream_to_encoder_surface(fov, mgr, oracle):
     assert np.array_equal(mgr.copy_to_host(np.empty((oh, ow), np.uint8), y), wy)
     assert np.array_equal(mgr.copy_to_host(np.empty((oh // 2, ow // 2), np.uint8), u), wu)
     assert np.array_equal(mgr.copy_to_host(np.empty((oh // 2, ow // 2), np.uint8), v), wv)
+
+
+# ---- YUV420P / NV12 -> RGB0 (video_decoder.cc:165-222) ---------------------------------------
+
+def to_rgb0(fov, mgr, y, u, v, nv12=False, pad=0, fill=0xEE):
+    H, W = y.shape
+    conv = fov.VideoFrameConverter(mgr)
+    y_ls, c_ls, d_ls = W + 3 * pad, (W if nv12 else W // 2) + 5 * pad, 4 * W + 8 * pad
+
+    def padded(a, ls):
+        b = np.zeros((a.shape[0], ls), np.uint8)
+        b[:, :a.shape[1]] = a
+        return b
+    dy = mgr.upload(padded(y, y_ls))
+    dst = mgr.upload(np.full((H, d_ls), fill, np.uint8))
+    if nv12:
+        uv = np.empty((H // 2, W), np.uint8)
+        uv[:, 0::2], uv[:, 1::2] = u, v
+        duv = mgr.upload(padded(uv, c_ls))
+        conv.NV12ToRGB0(dst, d_ls, dy, y_ls, duv, c_ls, W, H)
+    else:
+        du, dv = mgr.upload(padded(u, c_ls)), mgr.upload(padded(v, c_ls))
+        conv.YUV420PToRGB0(dst, d_ls, dy, y_ls, du, c_ls, dv, c_ls, W, H)
+    out = mgr.copy_to_host(np.empty((H, d_ls), np.uint8), dst)
+    assert (out[:, 4 * W:] == fill).all()
+    return out[:, :4 * W].reshape(H, W, 4)
+
+
+def test_decoder_small_case_matches_libswscale(fov, mgr):
+    g = np.load(os.path.join(GOLD, "swscale_small.npz"))
+    for nv12 in (False, True):
+        for pad in (0, 1):
+            got = to_rgb0(fov, mgr, g["dec_y"], g["dec_u"], g["dec_v"], nv12=nv12, pad=pad)
+            assert np.array_equal(got, g["dec_rgb0"]), (nv12, pad)
+
+
+def test_decoder_frame_sizes_match_libswscale_hashes(fov, mgr):
+    with open(os.path.join(GOLD, "swscale.json")) as fh:
+        cases = json.load(fh)["decode_cases"]
+    assert any(c["W"] == 7680 for c in cases)
+    for c in cases:
+        y, u, v = O.lcg_planes(c["W"], c["H"], c["seed"])
+        assert (O.fnv1a64(y), O.fnv1a64(u), O.fnv1a64(v)) == (c["y"], c["u"], c["v"])
+        assert O.fnv1a64(to_rgb0(fov, mgr, y, u, v)) == c["rgb0"], c
+        assert O.fnv1a64(to_rgb0(fov, mgr, y, u, v, nv12=True)) == c["rgb0"], c
+
+
+@pytest.mark.parametrize("W,H", [(2, 2), (6, 4), (18, 10), (130, 34), (258, 66)])
+def test_decoder_ragged_sizes_match_oracle(fov, mgr, oracle, W, H):
+    rng = np.random.default_rng(W * 77 + H)
+    y = rng.integers(0, 256, (H, W), dtype=np.uint8)
+    u = rng.integers(0, 256, (H // 2, W // 2), dtype=np.uint8)
+    v = rng.integers(0, 256, (H // 2, W // 2), dtype=np.uint8)
+    want = oracle.yuv420p_to_rgb0(y, u, v)
+    for nv12 in (False, True):
+        for pad in (0, 1):
+            assert np.array_equal(to_rgb0(fov, mgr, y, u, v, nv12=nv12, pad=pad), want), (nv12, pad)
+
+
+def test_decoder_batched_and_full_server_chain(fov, mgr, oracle):
+    """NV12 surfaces -> RGB0 -> SAT -> reduced buffer -> NV12: the server loop with both swscale
+    steps on the device (video_server.cc:291-345, video_encoder.cc:380-398), for n streams."""
+    n, W, H = 3, 256, 128
+    ow, oh = O.reduced_size(W), O.reduced_size(H)
+    rng = np.random.default_rng(5)
+    ys = rng.integers(0, 256, (n, H, W), dtype=np.uint8)
+    uvs = rng.integers(0, 256, (n, H // 2, W), dtype=np.uint8)
+    gaze = [(0.3, 0.4), (0.5, 0.5), (0.95, 0.1)]
+    conv, enc, dec = fov.VideoFrameConverter(mgr), fov.SATEncoder(mgr), fov.SATDecoder(mgr)
+    dy, duv = mgr.upload(ys), mgr.upload(uvs)
+    rgb = mgr.Buffer(n * H * W * 4)
+    sat = mgr.Buffer(n * H * W * 12)
+    red = mgr.upload(np.zeros((n, oh, ow, 4), np.uint8))
+    oy, ouv = mgr.Buffer(n * oh * ow), mgr.Buffer(n * oh * ow // 2)
+    conv.NV12ToRGB0Frames(n, rgb, H * W * 4, 4 * W, dy, H * W, W, duv, H * W // 2, W, W, H)
+    enc.EncodeFramesGPU(n, sat, H * W * 12, rgb, H * W * 4, W, H, 4 * W)
+    dec.SampleFramesRectGPU(n, red, oh * ow * 4, ow, oh, 4 * ow, sat, H * W * 12, W, H, gaze)
+    conv.RGB0ToNV12Frames(n, oy, oh * ow, ow, ouv, oh * ow // 2, ow, red, oh * ow * 4, 4 * ow, ow, oh)
+    got_rgb = mgr.copy_to_host(np.empty((n, H, W, 4), np.uint8), rgb)
+    got_y = mgr.copy_to_host(np.empty((n, oh, ow), np.uint8), oy)
+    got_uv = mgr.copy_to_host(np.empty((n, oh // 2, ow), np.uint8), ouv)
+    for f in range(n):
+        want_rgb = oracle.yuv420p_to_rgb0(ys[f], uvs[f][:, 0::2], uvs[f][:, 1::2])
+        assert np.array_equal(got_rgb[f], want_rgb)
+        want_red = oracle.sat_sample_rect(oracle.sat_encode(want_rgb), ow, oh, *gaze[f])
+        wy, wu, wv = oracle.rgb0_to_yuv420p(want_red)
+        assert np.array_equal(got_y[f], wy)
+        assert np.array_equal(got_uv[f][:, 0::2], wu) and np.array_equal(got_uv[f][:, 1::2], wv)
+
+
+def test_decoder_unsupported_sizes_are_rejected(fov, mgr):
+    conv = fov.VideoFrameConverter(mgr)
+    buf = mgr.Buffer(1 << 16)
+    for W, H in [(15, 8), (16, 9)]:
+        with pytest.raises(fov.FovError, match="even"):
+            conv.YUV420PToRGB0(buf, 256, buf, 64, buf, 64, buf, 64, W, H)
+    with pytest.raises(fov.FovError, match="invalid"):
+        conv.NV12ToRGB0(buf, 60, buf, 16, buf, 16, 16, 8)  # target linesize < 4 * width

@@ -219,3 +219,44 @@ def test_yuv420p_known_colours_and_size_contract(oracle):
     for W, H in [(15, 8), (16, 9), (16, 6), (0, 8)]:  # odd sizes / too few rows: other filters
         with pytest.raises(ValueError):
             oracle.rgb0_to_yuv420p(np.zeros((H, W, 4), np.uint8))
+
+
+# ---- YUV420P -> RGB0 (video_decoder.cc:165-222): pinned to the real libswscale ----------------
+
+def test_rgb0_from_yuv420p_small_matches_libswscale(oracle):
+    g = np.load(_golden_path("swscale_small.npz"))
+    assert np.array_equal(oracle.yuv420p_to_rgb0(g["dec_y"], g["dec_u"], g["dec_v"]), g["dec_rgb0"])
+
+
+def test_rgb0_from_yuv420p_hashes_match_libswscale(oracle):
+    import json
+    with open(_golden_path("swscale.json")) as fh:
+        cases = json.load(fh)["decode_cases"]
+    for c in cases:
+        if c["W"] > 3840:
+            continue  # 8K is covered on the GPU side
+        y, u, v = O.lcg_planes(c["W"], c["H"], c["seed"])
+        assert (O.fnv1a64(y), O.fnv1a64(u), O.fnv1a64(v)) == (c["y"], c["u"], c["v"])
+        assert O.fnv1a64(oracle.yuv420p_to_rgb0(y, u, v)) == c["rgb0"], c
+
+
+def test_rgb0_from_yuv420p_known_colours(oracle):
+    def planes(Y, U, V, W=8, H=4):
+        return (np.full((H, W), Y, np.uint8), np.full((H // 2, W // 2), U, np.uint8),
+                np.full((H // 2, W // 2), V, np.uint8))
+    # BT.601 limited range: black, white, below-black clips to 0, above-white to 255; alpha = 255
+    for yuv, rgb in [((16, 128, 128), (0, 0, 0)), ((235, 128, 128), (255, 255, 255)),
+                     ((0, 128, 128), (0, 0, 0)), ((255, 128, 128), (255, 255, 255)),
+                     ((126, 128, 128), (128, 128, 128))]:
+        out = oracle.yuv420p_to_rgb0(*planes(*yuv))
+        assert tuple(int(c) for c in out[1, 3, :3]) == rgb, (yuv, out[1, 3])
+        assert (out[..., 3] == 255).all()
+    # chroma is replicated over 2x2 blocks, not interpolated
+    y, u, v = planes(120, 128, 128, W=8, H=4)
+    u[0, 1], v[1, 2] = 30, 220
+    out = oracle.yuv420p_to_rgb0(y, u, v)
+    blocks = out.reshape(2, 2, 4, 2, 4)
+    assert (blocks == blocks[:, :1, :, :1]).all()
+    with pytest.raises(ValueError):
+        oracle.yuv420p_to_rgb0(np.zeros((3, 4), np.uint8), np.zeros((1, 2), np.uint8),
+                               np.zeros((1, 2), np.uint8))

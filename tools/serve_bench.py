@@ -37,6 +37,11 @@ ap.add_argument("--streams", type=int, default=64)
 ap.add_argument("--world", type=int, default=8, help="GPUs the streams are spread over")
 ap.add_argument("--frames", type=int, default=300)
 ap.add_argument("--workload", default="4k")
+ap.add_argument("--gaze-file", default=None,
+                help="GazeViewPoints trace (frame,<n>,forward,..,eye,..) replayed by every stream, "
+                     "stream s starting at record 7*s; default: per-stream random walks")
+ap.add_argument("--encoder-surface", action="store_true",
+                help="also convert every reduced buffer to NV12 (what the server hands to NVENC)")
 args = ap.parse_args()
 
 rank = int(os.environ.get("RANK", 0))
@@ -58,13 +63,29 @@ base = bench.synth_frame(W, H, 0)
 frames = np.stack([np.roll(base, 131 * s, axis=1) for s in mine])
 src, sat, red, full = m.upload(frames), m.Buffer(n * sb), m.Buffer(n * rb), m.Buffer(n * fb)
 m.memset(red, 0, n * rb)
-traces = np.stack([gaze_walk(s, args.frames + 3) for s in mine], axis=1)  # [frame][stream][2]
-for t in range(3):
+if args.gaze_file:
+    rec = fov.GazeViewPoints(args.gaze_file).gaze_array()
+    assert len(rec) > 0, "no records in " + args.gaze_file
+    idx = np.arange(args.frames + 3)
+    traces = np.stack([np.clip(rec[(idx + 7 * s) % len(rec)], 0.0, 1.0) for s in mine], axis=1)
+else:
+    traces = np.stack([gaze_walk(s, args.frames + 3) for s in mine], axis=1)  # [frame][stream][2]
+conv = fov.VideoFrameConverter(m)
+ny, nuv = (m.Buffer(n * ow * oh), m.Buffer(n * ow * oh // 2)) if args.encoder_surface else (None, None)
+
+
+def frame_time(t):
     fov.FoveateFramesGPU(m, n, full, fb, red, rb, sat, sb, src, fb, W, H, 4 * W, ow, oh, traces[t])
+    if args.encoder_surface:
+        conv.RGB0ToNV12Frames(n, ny, ow * oh, ow, nuv, ow * oh // 2, ow, red, rb, 4 * ow, ow, oh)
+
+
+for t in range(3):
+    frame_time(t)
 m.profile_reset()
 m.profile(True)
 for t in range(args.frames):
-    fov.FoveateFramesGPU(m, n, full, fb, red, rb, sat, sb, src, fb, W, H, 4 * W, ow, oh, traces[3 + t])
+    frame_time(3 + t)
 tot = m.profile_totals()
 m.profile(False)
 sec = sum(v[0] for v in tot.values()) / 1e3
@@ -73,7 +94,9 @@ if rank == 0:
     ranks = int(os.environ.get("WORLD_SIZE", 1)) if dist else 1
     print(json.dumps({
         "workload": "%d concurrent %s streams over %d GPU(s), stream s -> GPU s %% %d, %d frames each, "
-                    "random-walk gaze" % (args.streams, args.workload, world, world, args.frames),
+                    "%s gaze%s" % (args.streams, args.workload, world, world, args.frames,
+                                   "trace-file" if args.gaze_file else "random-walk",
+                                   ", NV12 encoder surface" if args.encoder_surface else ""),
         "gpus_measured": ranks, "streams_per_gpu": n,
         "frame_time_ms": round(sec / args.frames * 1e3, 4),
         "fps_per_stream": round(args.frames / sec, 1),
