@@ -39,20 +39,36 @@ struct YuvArgs {
 __device__ __forceinline__ int clip8(int v) { return min(max(v, 0), 255); }
 __device__ __forceinline__ int widen15(int v14) { return min(v14 * 2, 32767); }
 
+// c + k0 * byte0(p) + k1 * byte1(p) (lo) / c + k0 * byte2(p) + k1 * byte3(p) (hi): IDP.2A, the
+// 16-bit coefficients packed as {k0, k1}.  Exact 32-bit integer arithmetic.
+__device__ __forceinline__ int dp2a_lo(int k01, uint32_t p, int c) {
+  int d;
+  asm("dp2a.lo.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(k01), "r"(p), "r"(c));
+  return d;
+}
+__device__ __forceinline__ int dp2a_hi(int k01, uint32_t p, int c) {
+  int d;
+  asm("dp2a.hi.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(k01), "r"(p), "r"(c));
+  return d;
+}
+__host__ __device__ constexpr int pack16(int lo, int hi) { return (int)(((uint32_t)hi << 16) | ((uint32_t)lo & 0xffffu)); }
+
 __device__ __forceinline__ int luma8(uint32_t p) {
-  const int r = p & 0xff, g = (p >> 8) & 0xff, b = (p >> 16) & 0xff;
-  const int y14 = (kRY * r + kGY * g + kBY * b + (32 << 14) + 256) >> 9;
+  // R, G from bytes 0, 1; B from byte 2 (byte 3, the padding, is multiplied by 0)
+  const int y14 = dp2a_hi(pack16(kBY, 0), p, dp2a_lo(pack16(kRY, kGY), p, (32 << 14) + 256)) >> 9;
   return clip8((widen15(y14) + 64) >> 7);
 }
 
-// 15-bit chroma of one horizontal pixel pair
+// 15-bit chroma of one horizontal pixel pair: the matrix is linear, so the pair sum of the
+// reference is accumulated pixel by pixel
 __device__ __forceinline__ void chroma15(uint32_t p0, uint32_t p1, int &u15, int &v15) {
-  const int r = (p0 & 0xff) + (p1 & 0xff);
-  const int g = ((p0 >> 8) & 0xff) + ((p1 >> 8) & 0xff);
-  const int b = ((p0 >> 16) & 0xff) + ((p1 >> 16) & 0xff);
   constexpr int rnd = (256 << 15) + 512;
-  u15 = widen15((kRU * r + kGU * g + kBU * b + rnd) >> 10);
-  v15 = widen15((kRV * r + kGV * g + kBV * b + rnd) >> 10);
+  int u = dp2a_hi(pack16(kBU, 0), p0, dp2a_lo(pack16(kRU, kGU), p0, rnd));
+  u = dp2a_hi(pack16(kBU, 0), p1, dp2a_lo(pack16(kRU, kGU), p1, u));
+  int v = dp2a_hi(pack16(kBV, 0), p0, dp2a_lo(pack16(kRV, kGV), p0, rnd));
+  v = dp2a_hi(pack16(kBV, 0), p1, dp2a_lo(pack16(kRV, kGV), p1, v));
+  u15 = widen15(u >> 10);
+  v15 = widen15(v >> 10);
 }
 
 // One thread: 4 consecutive pixels x 2 rows of luma, 2 chroma samples.  Block (32, 8): the

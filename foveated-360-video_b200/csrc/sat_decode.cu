@@ -96,8 +96,16 @@ struct __align__(16) SampleRow {
                               // 2: its top edge is the bottom edge of the row above
 };
 
+// `.xyz =` store (:212): bytes 0..2 of the target pixel, byte 3 keeps its contents.  Two partial
+// stores (u16 + u8) instead of a read-modify-write of the pixel: the old pixel is never loaded, so
+// no warp waits on the target buffer.
+__device__ __forceinline__ void store_xyz(uint32_t *px, uint32_t rgb) {
+  asm volatile("st.global.u16 [%0], %1;" ::"l"(px), "h"((unsigned short)(rgb & 0xffffu)) : "memory");
+  asm volatile("st.global.u8 [%0+2], %1;" ::"l"(px), "r"((rgb >> 16) & 0xffu) : "memory");
+}
+
 #ifndef FOV360_SAMPLE_MIN_CTAS
-#define FOV360_SAMPLE_MIN_CTAS 5
+#define FOV360_SAMPLE_MIN_CTAS 6
 #endif
 template <int kSampleRows>
 __global__ void __launch_bounds__(32 * kSampleWarps, FOV360_SAMPLE_MIN_CTAS)
@@ -174,17 +182,15 @@ __global__ void __launch_bounds__(32 * kSampleWarps, FOV360_SAMPLE_MIN_CTAS)
       // box (mx, px] x (my, py] = the pixel (px, py): S(py,px) - S(my,px) - S(py,mx) + S(my,mx)
       const uint32_t *sp = reinterpret_cast<const uint32_t *>(
                                reinterpret_cast<const uint8_t *>(a.src) + (size_t)f * a.src_stride) + px;
-      uint32_t v[kSampleRows], o[kSampleRows];
+      uint32_t v[kSampleRows];
 #pragma unroll
       for (int r = 0; r < kSampleRows; ++r) {
         const bool on = live && (d[r].dyf & 1);
         v[r] = on ? __ldg(sp + (size_t)d[r].py * a.src_linesize_px) : 0u;
-        o[r] = on ? orow[(size_t)r * a.o_linesize_px] : 0u;
       }
 #pragma unroll
       for (int r = 0; r < kSampleRows; ++r)
-        if (live && (d[r].dyf & 1))
-          orow[(size_t)r * a.o_linesize_px] = (o[r] & 0xff000000u) | (v[r] & 0x00ffffffu);
+        if (live && (d[r].dyf & 1)) store_xyz(orow + (size_t)r * a.o_linesize_px, v[r]);
       return;
     }
   }
@@ -199,12 +205,6 @@ __global__ void __launch_bounds__(32 * kSampleWarps, FOV360_SAMPLE_MIN_CTAS)
   L[0] = ld_sat(sat, d[0].top_off + colL);
 #pragma unroll
   for (int r = 0; r < kSampleRows; ++r) L[r + 1] = ld_sat(sat, d[r].bot_off + colL);
-
-  // The store keeps byte 3 of the target pixel (`.xyz =`, :212): fetch the old pixels now too.
-  uint32_t old[kSampleRows];
-#pragma unroll
-  for (int r = 0; r < kSampleRows; ++r)
-    old[r] = (live && (d[r].dyf & 1)) ? orow[(size_t)r * a.o_linesize_px] : 0u;
 
 #pragma unroll
   for (int r = 0; r < kSampleRows; ++r, orow += a.o_linesize_px) {
@@ -230,8 +230,7 @@ __global__ void __launch_bounds__(32 * kSampleWarps, FOV360_SAMPLE_MIN_CTAS)
         s1 = udiv_exact(s1, area, rcp);
         s2 = udiv_exact(s2, area, rcp);
       }
-      // `.xyz =` store: byte 3 of the uchar4 keeps its previous value (:212).
-      *orow = (old[r] & 0xff000000u) | (s0 & 0xffu) | ((s1 & 0xffu) << 8) | ((s2 & 0xffu) << 16);
+      store_xyz(orow, (s0 & 0xffu) | ((s1 & 0xffu) << 8) | ((s2 & 0xffu) << 16));
     }
   }
 }
@@ -322,7 +321,7 @@ constexpr int kInterpMaxCols = 136;  // widest reduced-column window the generic
 constexpr int kInterpChunk = FOV360_INTERP_CHUNK;  // rows per pass of the periphery path
 constexpr int kInterpWarps = 4;      // warps per CTA, stacked vertically
 #ifndef FOV360_INTERP_MIN_CTAS
-#define FOV360_INTERP_MIN_CTAS 6
+#define FOV360_INTERP_MIN_CTAS 5
 #endif
 
 // Row descriptor, resolved by one lane per row, read back as one shared-memory broadcast.
@@ -963,7 +962,10 @@ cudaError_t launch_sat_sample_rect(const LaunchCtx &lc, int n, uint8_t *out, siz
   a.o_linesize_px = out_linesize / 4;  // :153
   a.W = W;
   a.H = H;
-  constexpr int kRows = 4;  // reduced rows per warp: 5 edges x 3 words in flight per lane
+#ifndef FOV360_SAMPLE_ROWS
+#define FOV360_SAMPLE_ROWS 4
+#endif
+  constexpr int kRows = FOV360_SAMPLE_ROWS;  // reduced rows per warp: kRows + 1 edges x 3 words in flight per lane
   const dim3 grid((ow + kSampleCols - 1) / kSampleCols,
                   (oh + kSampleWarps * kRows - 1) / (kSampleWarps * kRows), n),
       block(32, kSampleWarps);
