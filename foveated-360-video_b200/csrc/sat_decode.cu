@@ -310,10 +310,9 @@ __device__ __forceinline__ uint32_t pack_rgb0(uint32_t c0, uint32_t c1, uint32_t
 }
 
 constexpr int kInterpPx = 4;         // consecutive pixels per lane: one 16-byte store per row
-#ifndef FOV360_INTERP_ROWS
-#define FOV360_INTERP_ROWS 32
-#endif
-constexpr int kInterpRows = FOV360_INTERP_ROWS;  // rows per warp: the x-axis work is done once
+// Rows per warp are a template parameter of the kernel (32, 16 or 8): the x-axis work is done once
+// per warp, so large batches want tall tiles, while a single frame is less than one wave of CTAs
+// and finishes sooner with more, shorter ones.
 constexpr int kInterpMaxCols = 136;  // widest reduced-column window the generic path stages
 #ifndef FOV360_INTERP_CHUNK
 #define FOV360_INTERP_CHUNK 4
@@ -448,6 +447,7 @@ __device__ __forceinline__ uint32_t staged_px(const ulonglong2 v, const ulonglon
 //    colour is what the mixes select anyway, so V carries the sample's 4th byte along.
 //  * anything else (the warp straddles the edge of the 1:1 band, an exact hit that is not the
 //    selected tap, the +-W seam): generic row-by-row paths.
+template <int kInterpRows>
 __global__ void __launch_bounds__(32 * kInterpWarps, FOV360_INTERP_MIN_CTAS)
     sat_interpolate_rect_kernel(const InterpArgs a, const GazeBatch g) {
   constexpr int kStage =
@@ -520,14 +520,15 @@ __global__ void __launch_bounds__(32 * kInterpWarps, FOV360_INTERP_MIN_CTAS)
   // ---- y axis: one lane per row --------------------------------------------------------------
 #pragma unroll
   for (int rr = 0; rr < kInterpRows; rr += 32) {
-    const int y = min(y0 + rr + lane, H - 1);
+    const bool my_row = rr + lane < kInterpRows;  // tiles shorter than a warp: the other lanes idle
+    const int y = min(y0 + min(rr + lane, kInterpRows - 1), H - 1);
     const int dy = clampi(y - cyp, -H, H);
     const AxisSel sy = resolve_axis(load_entry(a.ly + (dy + H)), cyp, H, oh, false);
     const bool deg = sy.ratio == 0.0f || sy.ratio == 1.0f;
     const int sel = sy.ratio == 1.0f ? sy.hi : sy.lo;
     const int rlo = deg ? sel : sy.lo, rhi = deg ? sel : sy.hi;
     const int yex = sy.exact ? sy.exact_idx : -1;
-    simple = simple && (yex < 0 || (yex == rlo && rhi == rlo));
+    simple = simple && (!my_row || yex < 0 || (yex == rlo && rhi == rlo));
     const int pair = rlo | (rhi << 16);
     const int above = __shfl_up_sync(0xffffffffu, pair, 1);
     RowSel mine;
@@ -535,7 +536,7 @@ __global__ void __launch_bounds__(32 * kInterpWarps, FOV360_INTERP_MIN_CTAS)
     mine.off_hi = rhi * ow;
     mine.ty = sy.ratio;
     mine.info = (yex << 1) | ((lane == 0 || above != pair) ? 1 : 0);
-    rowsel[warp][rr + lane] = mine;
+    if (my_row) rowsel[warp][rr + lane] = mine;
   }
 
   uint32_t *orow = reinterpret_cast<uint32_t *>(a.out + (size_t)f * a.out_stride) +
@@ -989,11 +990,25 @@ cudaError_t launch_sat_interpolate_rect(const LaunchCtx &lc, int n, uint8_t *out
   a.H = H;
   a.ow = ow;
   a.oh = oh;
+  // Tile height by the amount of work: 32 rows per warp once the batch fills several waves of
+  // CTAs, 16 / 8 for a few frames / one small frame (measured on a B200: one 4K frame 0.046 ms with
+  // 32 rows, 0.026 with 8; eight 4K frames 0.125 / 0.116 ms with 32 / 16; four 8K frames 0.191 / 0.196).
+  const size_t px = (size_t)n * W * H;
+  static const int force_rows = [] {
+    const char *e = getenv("FOV360_INTERP_ROWS");
+    return e ? atoi(e) : 0;
+  }();
+  const int rows = force_rows ? force_rows : (px < ((size_t)16 << 20) ? 8 : (px < ((size_t)96 << 20) ? 16 : 32));
   const dim3 grid((W + 32 * kInterpPx - 1) / (32 * kInterpPx),
-                  (H + kInterpWarps * kInterpRows - 1) / (kInterpWarps * kInterpRows), n),
+                  (H + kInterpWarps * rows - 1) / (kInterpWarps * rows), n),
       block(32, kInterpWarps);
   KernelScope ks(lc, "sat_interpolate_rect");
-  sat_interpolate_rect_kernel<<<grid, block, 0, lc.stream>>>(a, gaze);
+  if (rows == 8)
+    sat_interpolate_rect_kernel<8><<<grid, block, 0, lc.stream>>>(a, gaze);
+  else if (rows == 16)
+    sat_interpolate_rect_kernel<16><<<grid, block, 0, lc.stream>>>(a, gaze);
+  else
+    sat_interpolate_rect_kernel<32><<<grid, block, 0, lc.stream>>>(a, gaze);
   return cudaGetLastError();
 }
 
