@@ -37,7 +37,6 @@ struct YuvArgs {
 };
 
 __device__ __forceinline__ int clip8(int v) { return min(max(v, 0), 255); }
-__device__ __forceinline__ int widen15(int v14) { return min(v14 * 2, 32767); }
 
 // c + k0 * byte0(p) + k1 * byte1(p) (lo) / c + k0 * byte2(p) + k1 * byte3(p) (hi): IDP.2A, the
 // 16-bit coefficients packed as {k0, k1}.  Exact 32-bit integer arithmetic.
@@ -53,42 +52,55 @@ __device__ __forceinline__ int dp2a_hi(int k01, uint32_t p, int c) {
 }
 __host__ __device__ constexpr int pack16(int lo, int hi) { return (int)(((uint32_t)hi << 16) | ((uint32_t)lo & 0xffffu)); }
 
+// The saturations and clips of the reference arithmetic cannot trigger for 8-bit input, which
+// collapses the per-sample work (the parity oracle keeps the literal form):
+//  * luma: t = RY r + GY g + BY b + (32 << 14) + 256 lies in [524544, 7700499], so y14 = t >> 9 is
+//    at most 15040, 2 * y14 never reaches 32767, and (2 * y14 + 64) >> 7 = (t + (32 << 9)) >> 15 lies
+//    in [16, 235];
+//  * chroma: c14 = (dot + (256 << 15) + 512) >> 10 lies in [1024, 15360] (again no saturation of
+//    2 * c14), and with the taps 512 * (1, 3, 3, 1)
+//    ((64 << 12) + sum tap_k * 2 c14_k) >> 19 = (c14_0 + 3 (c14_1 + c14_2) + c14_3 + 256) >> 9,
+//    which lies in [16, 240].
 __device__ __forceinline__ int luma8(uint32_t p) {
   // R, G from bytes 0, 1; B from byte 2 (byte 3, the padding, is multiplied by 0)
-  const int y14 = dp2a_hi(pack16(kBY, 0), p, dp2a_lo(pack16(kRY, kGY), p, (32 << 14) + 256)) >> 9;
-  return clip8((widen15(y14) + 64) >> 7);
+  return dp2a_hi(pack16(kBY, 0), p,
+                 dp2a_lo(pack16(kRY, kGY), p, (32 << 14) + 256 + (32 << 9))) >> 15;
 }
 
-// 15-bit chroma of one horizontal pixel pair: the matrix is linear, so the pair sum of the
+// 14-bit chroma of one horizontal pixel pair: the matrix is linear, so the pair sum of the
 // reference is accumulated pixel by pixel
-__device__ __forceinline__ void chroma15(uint32_t p0, uint32_t p1, int &u15, int &v15) {
+__device__ __forceinline__ void chroma14(uint32_t p0, uint32_t p1, int &u14, int &v14) {
   constexpr int rnd = (256 << 15) + 512;
   int u = dp2a_hi(pack16(kBU, 0), p0, dp2a_lo(pack16(kRU, kGU), p0, rnd));
   u = dp2a_hi(pack16(kBU, 0), p1, dp2a_lo(pack16(kRU, kGU), p1, u));
   int v = dp2a_hi(pack16(kBV, 0), p0, dp2a_lo(pack16(kRV, kGV), p0, rnd));
   v = dp2a_hi(pack16(kBV, 0), p1, dp2a_lo(pack16(kRV, kGV), p1, v));
-  u15 = widen15(u >> 10);
-  v15 = widen15(v >> 10);
+  u14 = u >> 10;
+  v14 = v >> 10;
 }
 
-// One thread: 4 consecutive pixels x 2 rows of luma, 2 chroma samples.  Block (32, 8): the
-// one-row halo above and below a thread's row pair is its neighbour's row pair, so the second
-// read of a row comes from L1.
+// One thread: 4 consecutive pixels x kYuvRows chroma rows (2 * kYuvRows frame rows).  All
+// 2 * kYuvRows + 2 frame rows the thread needs (its own plus one above and one below for the
+// vertical chroma filter) are requested before any is consumed - the kernel is bound by load
+// latency, not by arithmetic - and every row goes through the chroma matrix once per thread.
+constexpr int kYuvRows = 4;
+
 template <bool kNV12>
 __global__ void __launch_bounds__(256) rgb0_to_yuv_kernel(const YuvArgs a) {
   const int x0 = (blockIdx.x * 32 + threadIdx.x) * 4;
-  const int j = blockIdx.y * 8 + threadIdx.y;  // chroma row
+  const int j0 = (blockIdx.y * 8 + threadIdx.y) * kYuvRows;  // first chroma row
   const int W = a.W, H = a.H;
-  if (x0 >= W || 2 * j >= H) return;
+  if (x0 >= W || 2 * j0 >= H) return;
   const int f = blockIdx.z;
   const uint8_t *src = a.src + (size_t)f * a.src_stride;
   const bool full = x0 + 4 <= W;  // false only for the last thread of a row when W % 4 == 2
   const bool vec = full && ((reinterpret_cast<uintptr_t>(src) | (uintptr_t)a.src_ls) & 15) == 0;
+  constexpr int kRows = 2 * kYuvRows + 2;
 
-  uint32_t px[4][4];  // [source row 2j-1 .. 2j+2][pixel]
+  uint32_t px[kRows][4];  // frame rows 2*j0 - 1 .. 2*j0 + 2*kYuvRows, clamped to the frame
 #pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    const int yy = min(max(2 * j - 1 + k, 0), H - 1);
+  for (int k = 0; k < kRows; ++k) {
+    const int yy = min(max(2 * j0 - 1 + k, 0), H - 1);
     const uint8_t *row = src + (size_t)yy * a.src_ls + (size_t)x0 * 4;
     if (vec) {
       const uint4 q = __ldg(reinterpret_cast<const uint4 *>(row));
@@ -100,53 +112,57 @@ __global__ void __launch_bounds__(256) rgb0_to_yuv_kernel(const YuvArgs a) {
     }
   }
 
-  // luma: source rows 2j and 2j+1 are px[1] and px[2]
+  // 14-bit chroma of every row, both pairs
+  int cu[kRows][2], cv[kRows][2];
 #pragma unroll
-  for (int r = 0; r < 2; ++r) {
-    uint8_t *yrow = a.y + (size_t)f * a.y_stride + (size_t)(2 * j + r) * a.y_ls + x0;
-    const int l0 = luma8(px[1 + r][0]), l1 = luma8(px[1 + r][1]);
-    const int l2 = luma8(px[1 + r][2]), l3 = luma8(px[1 + r][3]);
-    if (full && (reinterpret_cast<uintptr_t>(yrow) & 3) == 0) {
-      *reinterpret_cast<uint32_t *>(yrow) = (uint32_t)l0 | (l1 << 8) | (l2 << 16) | (l3 << 24);
-    } else {
-      yrow[0] = (uint8_t)l0, yrow[1] = (uint8_t)l1;
-      if (full) yrow[2] = (uint8_t)l2, yrow[3] = (uint8_t)l3;
-    }
-  }
+  for (int k = 0; k < kRows; ++k)
+#pragma unroll
+    for (int p = 0; p < 2; ++p) chroma14(px[k][2 * p], px[k][2 * p + 1], cu[k][p], cv[k][p]);
 
-  // chroma: two pairs, 4 vertical taps each
-  int su[2] = {64 << 12, 64 << 12}, sv[2] = {64 << 12, 64 << 12};
 #pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    const int tap = (k == 0 || k == 3) ? 512 : 1536;
+  for (int t = 0; t < kYuvRows; ++t) {
+    const int j = j0 + t;
+    if (2 * j >= H) break;
+    // luma: frame rows 2j and 2j+1 are px[2t+1] and px[2t+2]
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const uint32_t *q = px[2 * t + 1 + r];
+      uint8_t *yrow = a.y + (size_t)f * a.y_stride + (size_t)(2 * j + r) * a.y_ls + x0;
+      const int l0 = luma8(q[0]), l1 = luma8(q[1]), l2 = luma8(q[2]), l3 = luma8(q[3]);
+      if (full && (reinterpret_cast<uintptr_t>(yrow) & 3) == 0) {
+        *reinterpret_cast<uint32_t *>(yrow) = (uint32_t)l0 | (l1 << 8) | (l2 << 16) | (l3 << 24);
+      } else {
+        yrow[0] = (uint8_t)l0, yrow[1] = (uint8_t)l1;
+        if (full) yrow[2] = (uint8_t)l2, yrow[3] = (uint8_t)l3;
+      }
+    }
+    // chroma: the vertical taps (1, 3, 3, 1) / 8 over frame rows 2j-1 .. 2j+2 = rows 2t .. 2t+3
+    int uu[2], vv[2];
 #pragma unroll
     for (int p = 0; p < 2; ++p) {
-      int cu, cv;
-      chroma15(px[k][2 * p], px[k][2 * p + 1], cu, cv);
-      su[p] += tap * cu;
-      sv[p] += tap * cv;
+      uu[p] = (cu[2 * t][p] + 3 * (cu[2 * t + 1][p] + cu[2 * t + 2][p]) + cu[2 * t + 3][p] + 256) >> 9;
+      vv[p] = (cv[2 * t][p] + 3 * (cv[2 * t + 1][p] + cv[2 * t + 2][p]) + cv[2 * t + 3][p] + 256) >> 9;
     }
-  }
-  const int u0 = clip8(su[0] >> 19), u1 = clip8(su[1] >> 19);
-  const int v0 = clip8(sv[0] >> 19), v1 = clip8(sv[1] >> 19);
-  const int cx = x0 / 2;
-  if (kNV12) {
-    uint8_t *c = a.u + (size_t)f * a.c_stride + (size_t)j * a.c_ls + (size_t)cx * 2;
-    if (full && (reinterpret_cast<uintptr_t>(c) & 3) == 0) {
-      *reinterpret_cast<uint32_t *>(c) = (uint32_t)u0 | (v0 << 8) | (u1 << 16) | (v1 << 24);
+    const int u0 = uu[0], u1 = uu[1], v0 = vv[0], v1 = vv[1];
+    const int cx = x0 / 2;
+    if (kNV12) {
+      uint8_t *c = a.u + (size_t)f * a.c_stride + (size_t)j * a.c_ls + (size_t)cx * 2;
+      if (full && (reinterpret_cast<uintptr_t>(c) & 3) == 0) {
+        *reinterpret_cast<uint32_t *>(c) = (uint32_t)u0 | (v0 << 8) | (u1 << 16) | (v1 << 24);
+      } else {
+        c[0] = (uint8_t)u0, c[1] = (uint8_t)v0;
+        if (full) c[2] = (uint8_t)u1, c[3] = (uint8_t)v1;
+      }
     } else {
-      c[0] = (uint8_t)u0, c[1] = (uint8_t)v0;
-      if (full) c[2] = (uint8_t)u1, c[3] = (uint8_t)v1;
-    }
-  } else {
-    uint8_t *up = a.u + (size_t)f * a.c_stride + (size_t)j * a.c_ls + cx;
-    uint8_t *vp = a.v + (size_t)f * a.c_stride + (size_t)j * a.v_ls + cx;
-    if (full && ((reinterpret_cast<uintptr_t>(up) | reinterpret_cast<uintptr_t>(vp)) & 1) == 0) {
-      *reinterpret_cast<uint16_t *>(up) = (uint16_t)(u0 | (u1 << 8));
-      *reinterpret_cast<uint16_t *>(vp) = (uint16_t)(v0 | (v1 << 8));
-    } else {
-      up[0] = (uint8_t)u0, vp[0] = (uint8_t)v0;
-      if (full) up[1] = (uint8_t)u1, vp[1] = (uint8_t)v1;
+      uint8_t *up = a.u + (size_t)f * a.c_stride + (size_t)j * a.c_ls + cx;
+      uint8_t *vp = a.v + (size_t)f * a.c_stride + (size_t)j * a.v_ls + cx;
+      if (full && ((reinterpret_cast<uintptr_t>(up) | reinterpret_cast<uintptr_t>(vp)) & 1) == 0) {
+        *reinterpret_cast<uint16_t *>(up) = (uint16_t)(u0 | (u1 << 8));
+        *reinterpret_cast<uint16_t *>(vp) = (uint16_t)(v0 | (v1 << 8));
+      } else {
+        up[0] = (uint8_t)u0, vp[0] = (uint8_t)v0;
+        if (full) up[1] = (uint8_t)u1, vp[1] = (uint8_t)v1;
+      }
     }
   }
 }
@@ -249,7 +265,7 @@ cudaError_t launch_rgb0_to_yuv(const LaunchCtx &lc, bool nv12, int n, uint8_t *y
   a.y_stride = y_stride, a.c_stride = c_stride, a.src_stride = src_stride;
   a.y_ls = y_ls, a.c_ls = u_ls, a.v_ls = v_ls, a.src_ls = src_ls;
   a.W = W, a.H = H;
-  const dim3 grid((W + 127) / 128, (H / 2 + 7) / 8, n), block(32, 8);
+  const dim3 grid((W + 127) / 128, (H / 2 + 8 * kYuvRows - 1) / (8 * kYuvRows), n), block(32, 8);
   KernelScope ks(lc, nv12 ? "rgb0_to_nv12" : "rgb0_to_yuv420p");
   if (nv12)
     rgb0_to_yuv_kernel<true><<<grid, block, 0, lc.stream>>>(a);

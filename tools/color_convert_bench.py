@@ -43,20 +43,40 @@ def nv12():
     conv.RGB0ToNV12Frames(B, y, ow * oh, ow, uv, ow * oh // 2, ow, red, 4 * ow * oh, 4 * ow, ow, oh)
 
 
+W2, H2 = W, H  # the decoder direction works on full frames
+dy, duv = m.upload(rng.integers(0, 256, (B, H2, W2), dtype=np.uint8)), \
+    m.upload(rng.integers(0, 256, (B, H2 // 2, W2), dtype=np.uint8))
+rgb = m.Buffer(B * W2 * H2 * 4)
+
+
+def decode_nv12():
+    conv.NV12ToRGB0Frames(B, rgb, W2 * H2 * 4, 4 * W2, dy, W2 * H2, W2, duv, W2 * H2 // 2, W2, W2, H2)
+
+
+def decode_planar():
+    conv.YUV420PToRGB0Frames(B, rgb, W2 * H2 * 4, 4 * W2, dy, W2 * H2, W2, duv, duv.at(B * W2 * H2 // 4),
+                             W2 * H2 // 4, W2 // 2, W2, H2)
+
+
 for _ in range(3):
     planar()
     nv12()
+    decode_nv12()
+    decode_planar()
 m.profile_reset()
 m.profile(True)
 for _ in range(args.steps):
     planar()
     nv12()
+    decode_nv12()
+    decode_planar()
 tot = m.profile_totals()
 m.profile(False)
 peak, _ = bench.peak_hbm_gbs()
-bytes_per_launch = B * ow * oh * 5.5  # 4 B/px read + 1.5 B/px written
 for k, (ms, cnt) in sorted(tot.items()):
     t = ms / cnt
+    w, h = (W2, H2) if k.endswith("to_rgb0") else (ow, oh)
+    bytes_per_launch = B * w * h * 5.5  # 4 B/px on the RGB0 side + 1.5 B/px on the YUV side
     print("%s %dx%d x%d: %.4f ms/launch, %.0f GB/s algorithmic (%.1f%% of the measured copy peak)" % (
-        k, ow, oh, B, t, bytes_per_launch / t / 1e6, 100 * bytes_per_launch / t / 1e6 / peak))
+        k, w, h, B, t, bytes_per_launch / t / 1e6, 100 * bytes_per_launch / t / 1e6 / peak))
 m.close()
