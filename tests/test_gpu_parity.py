@@ -337,6 +337,33 @@ def test_batched_pipeline_matches_single_calls(dev, fov, oracle):
         assert max_lsb(got_full[f][..., :3], w[..., :3]) <= INTERP_TOL, f
 
 
+def test_batch_larger_than_one_launch_carries(dev, fov, oracle):
+    """More frames than one launch carries gaze points for (64): the C ABI splits the batch, every
+    frame still gets its own gaze (the 64-stream serving configuration on a single GPU)."""
+    W, H, n = 256, 128, 70
+    ow, oh = fov.reduced_dim(W), fov.reduced_dim(H)
+    rng = np.random.default_rng(70)
+    gaze = rng.random((n, 2)).astype(np.float32)
+    base = O.smooth_frame(W, H, seed=9)
+    frames = np.stack([np.roll(base, 3 * f, axis=1) for f in range(n)])
+    src = dev.m.upload(frames)
+    sat = dev.m.Buffer(n * W * H * 12)
+    red = dev.m.upload(np.zeros((n, oh, ow, 4), np.uint8))
+    full = dev.m.Buffer(n * W * H * 4)
+    fov.FoveateFramesGPU(dev.m, n, full, W * H * 4, red, ow * oh * 4, sat, W * H * 12, src,
+                         W * H * 4, W, H, 4 * W, ow, oh, gaze)
+    got_sat = dev.m.copy_to_host(np.empty((n, H, W, 3), np.uint32), sat)
+    got_red = dev.m.copy_to_host(np.empty((n, oh, ow, 4), np.uint8), red)
+    got_full = dev.m.copy_to_host(np.empty((n, H, W, 4), np.uint8), full)
+    for f in range(n):
+        s = oracle.sat_encode(frames[f])
+        assert np.array_equal(got_sat[f], s), f
+        r = oracle.sat_sample_rect(s, ow, oh, float(gaze[f, 0]), float(gaze[f, 1]))
+        assert np.array_equal(got_red[f], r), f
+        w = oracle.sat_interpolate_rect(r, W, H, float(gaze[f, 0]), float(gaze[f, 1]))
+        assert max_lsb(got_full[f][..., :3], w[..., :3]) <= INTERP_TOL, f
+
+
 def test_fused_pipeline_unit_boxes_read_source(dev, fov, oracle):
     """fov_sat_foveate_batched reads 1x1 boxes from the source frame instead of the SAT: same bits,
     also with a non-zero 4th source byte, a prefilled reduced buffer and gazes on the borders."""
