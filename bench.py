@@ -423,7 +423,7 @@ def main():
     ap.add_argument("--workload", default="8k", choices=sorted(WORKLOADS))
     ap.add_argument("--batch", type=int, default=16,
                     help="frames per step per GPU (SURVEY 8(d): cfg3 is a batch of 16 frames)")
-    ap.add_argument("--e2e-depth", type=int, default=3)
+    ap.add_argument("--e2e-depth", type=int, default=6)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
