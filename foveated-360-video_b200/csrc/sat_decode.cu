@@ -319,6 +319,7 @@ constexpr int kInterpMaxCols = 136;  // widest reduced-column window the generic
 #endif
 constexpr int kInterpChunk = FOV360_INTERP_CHUNK;  // rows per pass of the periphery path
 constexpr int kInterpWarps = 4;      // warps per CTA, stacked vertically
+constexpr int kCopyRows = 4;         // copy rows requested per batch: 6 or 8 spill and are slower
 #ifndef FOV360_INTERP_MIN_CTAS
 #define FOV360_INTERP_MIN_CTAS 5
 #endif
@@ -464,6 +465,13 @@ __global__ void __launch_bounds__(32 * kInterpWarps, FOV360_INTERP_MIN_CTAS)
   const int cyp = gaze_px(g.xy[2 * f + 1], H);
   const uint32_t *red = reinterpret_cast<const uint32_t *>(a.red + (size_t)f * a.red_stride);
 
+  // Both table entries a lane needs - the x entry of its pixel slot and the y entry of its row - are
+  // requested before either is used: the prologue is two L2 latencies deep otherwise.
+  static_assert(kInterpRows <= 32, "one lane per row of the warp's tile");
+  const bool my_row = lane < kInterpRows;  // tiles shorter than a warp: the other lanes idle
+  const int yrow = min(y0 + min(lane, kInterpRows - 1), H - 1);
+  const InterpEntry ey = load_entry(a.ly + (clampi(yrow - cyp, -H, H) + H));
+
   // ---- x axis: resolved once per CTA (its warps cover the same 128 columns): warp k resolves
   // pixel k of every lane --------------------------------------------------------------------
   static_assert(kInterpWarps == kInterpPx, "one warp per pixel slot");
@@ -518,12 +526,8 @@ __global__ void __launch_bounds__(32 * kInterpWarps, FOV360_INTERP_MIN_CTAS)
   const int ncols = cmax - cmin + 1;
 
   // ---- y axis: one lane per row --------------------------------------------------------------
-#pragma unroll
-  for (int rr = 0; rr < kInterpRows; rr += 32) {
-    const bool my_row = rr + lane < kInterpRows;  // tiles shorter than a warp: the other lanes idle
-    const int y = min(y0 + min(rr + lane, kInterpRows - 1), H - 1);
-    const int dy = clampi(y - cyp, -H, H);
-    const AxisSel sy = resolve_axis(load_entry(a.ly + (dy + H)), cyp, H, oh, false);
+  {
+    const AxisSel sy = resolve_axis(ey, cyp, H, oh, false);
     const bool deg = sy.ratio == 0.0f || sy.ratio == 1.0f;
     const int sel = sy.ratio == 1.0f ? sy.hi : sy.lo;
     const int rlo = deg ? sel : sy.lo, rhi = deg ? sel : sy.hi;
@@ -536,7 +540,7 @@ __global__ void __launch_bounds__(32 * kInterpWarps, FOV360_INTERP_MIN_CTAS)
     mine.off_hi = rhi * ow;
     mine.ty = sy.ratio;
     mine.info = (yex << 1) | ((lane == 0 || above != pair) ? 1 : 0);
-    if (my_row) rowsel[warp][rr + lane] = mine;
+    if (my_row) rowsel[warp][lane] = mine;
   }
 
   uint32_t *orow = reinterpret_cast<uint32_t *>(a.out + (size_t)f * a.out_stride) +
@@ -584,16 +588,16 @@ __global__ void __launch_bounds__(32 * kInterpWarps, FOV360_INTERP_MIN_CTAS)
         // Copy rows (integer-valued taps: l + (r - l) == r) come in long runs: four rows of loads
         // in flight per batch.
         int nb = 1;
-        RowSel b[4];
+        RowSel b[kCopyRows];
         b[0] = rs;
 #pragma unroll
-        for (int j = 1; j < 4; ++j) {
+        for (int j = 1; j < kCopyRows; ++j) {
           b[j] = rowsel[warp][min(r + j, kInterpRows - 1)];
           if (nb == j && r + j < nrows && b[j].off_lo == b[j].off_hi) nb = j + 1;
         }
-        uint32_t px[4][kInterpPx];
+        uint32_t px[kCopyRows][kInterpPx];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
+        for (int j = 0; j < kCopyRows; ++j) {
           if (j < nb) {
             const bool yhit = b[j].info >= 0;  // exact-hit row index is not -1
 #pragma unroll
@@ -602,7 +606,7 @@ __global__ void __launch_bounds__(32 * kInterpWarps, FOV360_INTERP_MIN_CTAS)
           }
         }
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
+        for (int j = 0; j < kCopyRows; ++j) {
           if (j < nb) {
             store_row(px[j]);
             orow += W;
