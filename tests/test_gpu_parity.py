@@ -349,6 +349,43 @@ def test_roundtrip_identity_near_gaze_8k(dev):
         assert np.array_equal(full[win], frame[win]), (cx, cy)
 
 
+def test_bench_configuration_full_size_bit_exact(dev, fov, oracle):
+    """The benchmark's own workload - BASELINE configs[2]: 16 frames of 7680x3840 with per-frame
+    gaze through one fov_sat_foveate_batched call - against the oracle, frame by frame: SAT,
+    reduced buffer and un-warped frame bit-exact at full size."""
+    W, H, n = 7680, 3840, 16
+    ow, oh = fov.reduced_dim(W), fov.reduced_dim(H)
+    assert (ow, oh) == (4272, 2144)
+    rng = np.random.default_rng(16)
+    gaze = rng.random((n, 2)).astype(np.float32)
+    gaze[0], gaze[1], gaze[2] = (0.5, 0.5), (0.0, 1.0), (0.999, 0.02)  # centre, corner, seam
+    base = O.lcg_frame(W, H, 8192)
+    fb, sb, rb = W * H * 4, W * H * 12, ow * oh * 4
+    src = dev.m.Buffer(n * fb)
+    for f in range(n):
+        dev.m.copy_to_device(src, np.roll(base, 131 * f, axis=1), dst_offset=f * fb)
+    sat, red, full = dev.m.Buffer(n * sb), dev.m.Buffer(n * rb), dev.m.Buffer(n * fb)
+    dev.m.memset(red, 0, n * rb)
+    fov.FoveateFramesGPU(dev.m, n, full, fb, red, rb, sat, sb, src, fb, W, H, 4 * W, ow, oh, gaze)
+    got_sat = np.empty((H, W, 3), np.uint32)
+    got_red = np.empty((oh, ow, 4), np.uint8)
+    got_full = np.empty((H, W, 4), np.uint8)
+    for f in range(n):
+        frame = np.roll(base, 131 * f, axis=1)
+        cx, cy = float(gaze[f, 0]), float(gaze[f, 1])
+        want_sat = oracle.sat_encode(frame)
+        dev.m.copy_to_host(got_sat, sat, src_offset=f * sb)
+        assert np.array_equal(got_sat, want_sat), f
+        want_red = oracle.sat_sample_rect(want_sat, ow, oh, cx, cy)
+        dev.m.copy_to_host(got_red, red, src_offset=f * rb)
+        assert np.array_equal(got_red, want_red), f
+        want_full = oracle.sat_interpolate_rect(want_red, W, H, cx, cy)
+        dev.m.copy_to_host(got_full, full, src_offset=f * fb)
+        assert np.array_equal(got_full, want_full), f
+    for b in (src, sat, red, full):
+        b.free()
+
+
 def test_batched_pipeline_matches_single_calls(dev, fov, oracle):
     """configs[2] shape: batched frames with per-frame gaze through fov_sat_foveate_batched."""
     W, H, n = 1280, 720, 6
