@@ -427,6 +427,20 @@ __device__ __forceinline__ uint32_t staged_px(const ulonglong2 v, const ulonglon
   return lerp_px2(v, d, pack2(t, t)) | (vw & keep_lo) | (dw & keep_hi);
 }
 
+// The same from a staged column v and its right neighbour n (D = n - v is formed here, bit for bit
+// what pass 1 would have stored): 4th byte from v.w or n.w.
+__device__ __forceinline__ uint32_t staged_px_vn(const ulonglong2 v, const ulonglong2 d,
+                                                 const ulonglong2 n, float t, uint32_t keep_lo,
+                                                 uint32_t keep_hi) {
+  uint32_t vz, vw, nz, nw;
+  unpack2(v.y, vz, vw);
+  unpack2(n.y, nz, nw);
+  return lerp_px2(v, d, pack2(t, t)) | (vw & keep_lo) | (nw & keep_hi);
+}
+__device__ __forceinline__ ulonglong2 sub_cols(const ulonglong2 n, const ulonglong2 v) {
+  return make_ulonglong2(sub2_rn(n.x, v.x), sub2_rn(n.y, v.y));  // the .w halves are never used
+}
+
 // interpolate_rect, one warp = 128 columns x kInterpRows rows.
 //
 // Everything that depends on x only (table entry, wrap, border fix-ups, clamped reduced columns,
@@ -728,22 +742,20 @@ __global__ void __launch_bounds__(32 * kInterpWarps, FOV360_INTERP_MIN_CTAS)
         rawq[j] = __ldg(rcol + rs.off_hi);
       }
     };
-    // packed pass 1: {V.x, V.y} and {V.z, alpha} are the two 8-byte halves of the staged float4
+    // packed pass 1: {V.x, V.y} and {V.z, alpha} are the two 8-byte halves of the staged float4.
+    // Only V is staged (kStride slots per row: the window's 32 columns and one copy of the last for
+    // the right neighbour of column 31); pass 2 forms D = V[c+1] - V[c] for the columns it uses.
+    constexpr int kStride = 34;
+    static_assert(kInterpChunk * kStride <= kStage, "staged rows must fit the staging area");
     auto stage_row = [&](int j, const RowSel rs) {
       const f32x2 ty2 = pack2(rs.ty, rs.ty);
       const f32x2 v01 = add2_rn(pack2(tp.p[0], tp.p[1]), mul2_rn(pack2(tp.d[0], tp.d[1]), ty2));
       const float v2 = lerp_rn(tp.p[2], tp.d[2], rs.ty);
       const uint32_t alpha = rs.info >= 0 ? (rawp[j] & 0xff000000u) : 0u;
-      const f32x2 v2a = pack2(v2, __uint_as_float(alpha));
-      const f32x2 n01 = __shfl_down_sync(0xffffffffu, v01, 1);
-      const f32x2 n2a = __shfl_down_sync(0xffffffffu, v2a, 1);
-      uint32_t n2, alpha_next, d2;
-      unpack2(n2a, n2, alpha_next);
-      d2 = __float_as_uint(__fsub_rn(__uint_as_float(n2), v2));
-      ulonglong2 *dst = reinterpret_cast<ulonglong2 *>(vs);
-      dst[j * 32 + lane] = make_ulonglong2(v01, v2a);
-      dst[(kInterpChunk + j) * 32 + lane] =
-          make_ulonglong2(sub2_rn(n01, v01), pack2(__uint_as_float(d2), __uint_as_float(alpha_next)));
+      const ulonglong2 val = make_ulonglong2(v01, pack2(v2, __uint_as_float(alpha)));
+      ulonglong2 *dst = reinterpret_cast<ulonglong2 *>(vs) + j * kStride;
+      dst[lane] = val;
+      if (lane == 31) dst[32] = val;
     };
     request(0);
     for (int r0 = 0; r0 < nrows; r0 += kInterpChunk) {
@@ -774,23 +786,25 @@ __global__ void __launch_bounds__(32 * kInterpWarps, FOV360_INTERP_MIN_CTAS)
       for (int j = 0; j < kInterpChunk; ++j) {
         uint32_t px[kInterpPx];
         if (two_cols) {  // warp-uniform: columns of pixels 1 and 2 are those of pixel 0 or pixel 3
-          const ulonglong2 va = *reinterpret_cast<const ulonglong2 *>(pv[0] + j * 32);
-          const ulonglong2 da = *reinterpret_cast<const ulonglong2 *>(pv[0] + (kInterpChunk + j) * 32);
-          const ulonglong2 vb = *reinterpret_cast<const ulonglong2 *>(pv[3] + j * 32);
-          const ulonglong2 db = *reinterpret_cast<const ulonglong2 *>(pv[3] + (kInterpChunk + j) * 32);
+          const ulonglong2 va = *reinterpret_cast<const ulonglong2 *>(pv[0] + j * kStride);
+          const ulonglong2 na = *reinterpret_cast<const ulonglong2 *>(pv[0] + j * kStride + 1);
+          const ulonglong2 vb = *reinterpret_cast<const ulonglong2 *>(pv[3] + j * kStride);
+          const ulonglong2 nb = *reinterpret_cast<const ulonglong2 *>(pv[3] + j * kStride + 1);
+          const ulonglong2 da = sub_cols(na, va), db = sub_cols(nb, vb);
 #pragma unroll
           for (int k = 0; k < kInterpPx; ++k) {
             const bool b = k == 3 || (k > 0 && use_b[k]);
-            px[k] = staged_px(make_ulonglong2(b ? vb.x : va.x, b ? vb.y : va.y),
-                              make_ulonglong2(b ? db.x : da.x, b ? db.y : da.y), xr[k], keep_lo[k],
-                              keep_hi[k]);
+            px[k] = staged_px_vn(make_ulonglong2(b ? vb.x : va.x, b ? vb.y : va.y),
+                                 make_ulonglong2(b ? db.x : da.x, b ? db.y : da.y),
+                                 make_ulonglong2(0ull, b ? nb.y : na.y), xr[k], keep_lo[k], keep_hi[k]);
           }
         } else {
 #pragma unroll
-          for (int k = 0; k < kInterpPx; ++k)
-            px[k] = staged_px(*reinterpret_cast<const ulonglong2 *>(pv[k] + j * 32),
-                              *reinterpret_cast<const ulonglong2 *>(pv[k] + (kInterpChunk + j) * 32),
-                              xr[k], keep_lo[k], keep_hi[k]);
+          for (int k = 0; k < kInterpPx; ++k) {
+            const ulonglong2 v = *reinterpret_cast<const ulonglong2 *>(pv[k] + j * kStride);
+            const ulonglong2 n = *reinterpret_cast<const ulonglong2 *>(pv[k] + j * kStride + 1);
+            px[k] = staged_px_vn(v, sub_cols(n, v), n, xr[k], keep_lo[k], keep_hi[k]);
+          }
         }
         if (r0 + j < nrows) __stcs(orow4, make_uint4(px[0], px[1], px[2], px[3]));
         orow4 += W / 4;
