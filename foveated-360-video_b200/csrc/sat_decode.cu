@@ -465,9 +465,11 @@ __device__ __forceinline__ ulonglong2 sub_cols(const ulonglong2 n, const ulonglo
 template <int kInterpRows>
 __global__ void __launch_bounds__(32 * kInterpWarps, FOV360_INTERP_MIN_CTAS)
     sat_interpolate_rect_kernel(const InterpArgs a, const GazeBatch g) {
+  // staging area of a warp: kInterpChunk rows of V (34 slots each) in the periphery path, one row
+  // of V and D (kInterpMaxCols each) in the wide-window path
   constexpr int kStage =
-      2 * (kInterpChunk * 32 > kInterpMaxCols ? kInterpChunk * 32 : kInterpMaxCols);
-  __shared__ float4 vstage[kInterpWarps][kStage];  // V and D of the column window
+      kInterpChunk * 34 > 2 * kInterpMaxCols ? kInterpChunk * 34 : 2 * kInterpMaxCols;
+  __shared__ float4 vstage[kInterpWarps][kStage];
   __shared__ RowSel rowsel[kInterpWarps][kInterpRows];
   __shared__ int4 xsel[kInterpPx][32];
   const int lane = threadIdx.x, warp = threadIdx.y;
