@@ -27,7 +27,7 @@ LIB_PATH = os.path.join(HERE, "libfov360.so")
 SOURCES = ["capi.cu", "sat_encode.cu", "sat_onepass.cu", "sat_decode.cu", "image_sampler.cu",
            "projections.cu", "color_convert.cu", "luts.cc"]
 HEADERS = [os.path.join(CSRC, "fov360_internal.h"), os.path.join(CSRC, "sat_common.cuh"),
-           os.path.join(CSRC, "projection_common.cuh"),
+           os.path.join(CSRC, "projection_common.cuh"), os.path.join(CSRC, "pixel_math.cuh"),
            os.path.join(INCLUDE, "fov360.h")]
 
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]

@@ -5,6 +5,7 @@
 #include <cstdio>
 #include <cstring>
 #include <memory>
+#include <unordered_set>
 
 #include "fov360_internal.h"
 
@@ -19,14 +20,16 @@ struct fov_ctx {
   Profiler prof;
   LaunchCtx lc() { return LaunchCtx{stream, sm_count, device, &prof, &launches}; }
   SatScratch sat_scratch;
-  std::tuple<int, int, int, int, int> sat_layout{0, 0, 0, 0, 0};  // (n, W, H, R, NW) of the flags
-  uint32_t sat_epoch = 0;
+  bool sat_scratch_dirty = true;  // holds bytes that are not carry units of an earlier epoch
+  uint32_t sat_epoch = 0;         // grows monotonically: one value per one-pass launch
   std::map<std::tuple<int, int, int, int>, SatGrid> sat_grids;
   std::map<std::tuple<int, int, int, int>, InterpLut> interp_luts;
   std::map<std::tuple<int, int, int, int>, ImgGrid> img_grids;
   std::map<std::tuple<int, int>, LogpolarGrid> lp_grids;
   // The reference objects hold ONE current grid; lazily-initialised samplers use it.
   const SatGrid *cur_sat_grid = nullptr;
+  // device allocations handed out by fov_malloc and not yet freed: released with the context
+  std::unordered_set<void *> allocations;
 };
 
 namespace fov {
@@ -38,8 +41,19 @@ cudaEvent_t Profiler::get() {
     return e;
   }
   cudaEvent_t e = nullptr;
-  cudaEventCreate(&e);
+  if (cudaEventCreate(&e) != cudaSuccess) return nullptr;  // the launch is then not timed
   return e;
+}
+
+// Pairs whose second event has completed are folded into the totals without waiting for anything.
+void Profiler::recycle() {
+  size_t done = 0;
+  while (done < pending.size() && cudaEventQuery(pending[done].b) == cudaSuccess) ++done;
+  if (!done) return;
+  std::vector<Pending> rest(pending.begin() + done, pending.end());
+  pending.resize(done);
+  collect();
+  pending.swap(rest);
 }
 
 void Profiler::collect() {
@@ -66,7 +80,9 @@ void Profiler::release() {
 
 namespace {
 
-std::string g_global_error;
+// errors raised without a context (creation failures, calls on a null context): per thread, like
+// errno - connection threads fail independently
+thread_local std::string g_global_error;
 
 int fail(fov_ctx *ctx, int code, const std::string &msg) {
   if (ctx)
@@ -89,8 +105,25 @@ int cuda_fail(fov_ctx *ctx, cudaError_t e, const char *what) {
     if (e_ != cudaSuccess) return cuda_fail(ctx, e_, what); \
   } while (0)
 
+// Makes the context's device current for the duration of a call and restores the caller's: a
+// server thread that also drives NVENC / NVDEC on another GPU keeps its own current device.
 struct DeviceGuard {
-  explicit DeviceGuard(const fov_ctx *c) { cudaSetDevice(c->device); }
+  explicit DeviceGuard(const fov_ctx *c) {
+    if (cudaGetDevice(&prev_) != cudaSuccess) prev_ = -1;
+    if (prev_ != c->device) {
+      cudaSetDevice(c->device);
+      switched_ = true;
+    }
+  }
+  ~DeviceGuard() {
+    if (switched_ && prev_ >= 0) cudaSetDevice(prev_);
+  }
+  DeviceGuard(const DeviceGuard &) = delete;
+  DeviceGuard &operator=(const DeviceGuard &) = delete;
+
+ private:
+  int prev_ = -1;
+  bool switched_ = false;
 };
 
 template <class T>
@@ -173,16 +206,21 @@ int get_lp_grid(fov_ctx *ctx, int ow, int oh, const LogpolarGrid **out) {
     std::vector<double2> dir;
     build_logpolar_directions(oh, dir);
     FOV_CUDA(ctx, upload(ctx, &g.d_dir, dir), "logpolar grid upload");
+    std::vector<double> radius64(g.h_radius.begin(), g.h_radius.end());
+    FOV_CUDA(ctx, upload(ctx, &g.d_radius_f64, radius64), "logpolar grid upload");
+    std::vector<double2> lntab;
+    build_logpolar_lntab(ow, lntab);
+    FOV_CUDA(ctx, upload(ctx, &g.d_lntab, lntab), "logpolar grid upload");
     it = ctx->lp_grids.emplace(key, std::move(g)).first;
   }
   *out = &it->second;
   return FOV_OK;
 }
 
-int ensure_sat_scratch(fov_ctx *ctx, int n, int W, int H) {
-  size_t need = sat_scratch_bytes(n, W, H);
-  const size_t need1 = sat_onepass_plan(n, W, H).bytes;
-  if (need1 > need) need = need1;
+// Scratch of the path the call takes (one-pass plan or the three-kernel fallback): they never run
+// in the same call, and the larger of the two would double the footprint of a batch of 8K frames.
+int ensure_sat_scratch(fov_ctx *ctx, int n, int W, int H, bool onepass) {
+  const size_t need = onepass ? sat_onepass_plan(n, W, H).bytes : sat_scratch_bytes(n, W, H);
   if (need <= ctx->sat_scratch.bytes) return FOV_OK;
   if (ctx->sat_scratch.base) {
     FOV_CUDA(ctx, cudaStreamSynchronize(ctx->stream), "sat scratch resize");
@@ -191,7 +229,7 @@ int ensure_sat_scratch(fov_ctx *ctx, int n, int W, int H) {
   }
   FOV_CUDA(ctx, cudaMalloc(&ctx->sat_scratch.base, need), "sat scratch alloc");
   ctx->sat_scratch.bytes = need;
-  ctx->sat_layout = std::make_tuple(0, 0, 0, 0, 0);  // forces the flag arrays to be cleared
+  ctx->sat_scratch_dirty = true;  // fresh memory: anything could look like a tag
   return FOV_OK;
 }
 
@@ -218,10 +256,11 @@ fov_ctx *fov_ctx_create(int device, int *err) {
                std::string("fov360: no usable CUDA device (there is no CPU fallback): ") +
                    (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0"));
   if (device < 0 || device >= n) return set(FOV_ERR_INVALID, "fov360: device index out of range");
-  e = cudaSetDevice(device);
-  if (e != cudaSuccess) return set((int)e, std::string("cudaSetDevice: ") + cudaGetErrorString(e));
   std::unique_ptr<fov_ctx> ctx(new fov_ctx);
   ctx->device = device;
+  DeviceGuard g(ctx.get());  // the caller's current device is restored on return
+  if ((e = cudaGetLastError()) != cudaSuccess)
+    return set((int)e, std::string("cudaSetDevice: ") + cudaGetErrorString(e));
   cudaDeviceProp prop;
   if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
   e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
@@ -252,8 +291,11 @@ void fov_ctx_destroy(fov_ctx *ctx) {
     cudaFree(kv.second.d_cos);
     cudaFree(kv.second.d_sin);
     cudaFree(kv.second.d_dir);
+    cudaFree(kv.second.d_radius_f64);
+    cudaFree(kv.second.d_lntab);
   }
   if (ctx->sat_scratch.base) cudaFree(ctx->sat_scratch.base);
+  for (void *p : ctx->allocations) cudaFree(p);  // buffers the caller never returned
   ctx->prof.release();
   cudaStreamDestroy(ctx->stream);
   delete ctx;
@@ -321,12 +363,19 @@ int fov_malloc(fov_ctx *ctx, void **dptr, size_t nbytes) {
   if (!dptr) return fail(ctx, FOV_ERR_INVALID, "fov_malloc: null output pointer");
   DeviceGuard g(ctx);
   FOV_CUDA(ctx, cudaMalloc(dptr, nbytes ? nbytes : 1), "fov_malloc");
+  ctx->allocations.insert(*dptr);
   return FOV_OK;
 }
 
+// Stream-ordered: the buffer is released once the work already queued on the context's stream
+// has run; the host does not wait (clReleaseMemObject semantics).
 int fov_free(fov_ctx *ctx, void *dptr) {
   FOV_REQUIRE_CTX(ctx);
+  if (!dptr) return FOV_OK;
   DeviceGuard g(ctx);
+  ctx->allocations.erase(dptr);
+  if (cudaFreeAsync(dptr, ctx->stream) == cudaSuccess) return FOV_OK;
+  (void)cudaGetLastError();  // not a stream-orderable allocation on this driver: wait, then free
   FOV_CUDA(ctx, cudaStreamSynchronize(ctx->stream), "fov_free");
   FOV_CUDA(ctx, cudaFree(dptr), "fov_free");
   return FOV_OK;
@@ -399,16 +448,16 @@ int fov_sat_encode_batched(fov_ctx *ctx, int n, uint32_t *sat, size_t sat_stride
     return fail(ctx, FOV_ERR_INVALID, "fov_sat_encode: SAT buffer must be 4-byte aligned");
   if (n > 65535) return fail(ctx, FOV_ERR_INVALID, "fov_sat_encode: batch too large");
   DeviceGuard g(ctx);
-  int rc = ensure_sat_scratch(ctx, n, W, H);
+  const bool onepass = sat_onepass_eligible(sat, sat_stride, src, src_stride, W, H, linesize);
+  int rc = ensure_sat_scratch(ctx, n, W, H, onepass);
   if (rc) return rc;
-  if (sat_onepass_eligible(sat, sat_stride, src, src_stride, W, H, linesize)) {
-    const SatOnePassPlan p = sat_onepass_plan(n, W, H);
-    const auto key = std::make_tuple(n, W, H, p.R, p.NW);
-    if (key != ctx->sat_layout || ctx->sat_epoch >= 0x3ffffff0u) {
-      // new tile geometry (or epoch wrap): the ticket counters and carry flags start from zero
-      FOV_CUDA(ctx, cudaMemsetAsync(ctx->sat_scratch.base, 0, p.clear_bytes, ctx->stream),
+  if (onepass) {
+    if (ctx->sat_scratch_dirty || ctx->sat_epoch >= 0x3ffffff0u) {
+      // Ticket counters and carry tags start from zero.  Alternating geometries or batch sizes need
+      // no clear: tags carry a context-wide epoch, so units of other layouts are simply stale.
+      FOV_CUDA(ctx, cudaMemsetAsync(ctx->sat_scratch.base, 0, ctx->sat_scratch.bytes, ctx->stream),
                "sat scratch clear");
-      ctx->sat_layout = key;
+      ctx->sat_scratch_dirty = false;
       ctx->sat_epoch = 0;
     }
     FOV_CUDA(ctx,
@@ -418,7 +467,7 @@ int fov_sat_encode_batched(fov_ctx *ctx, int n, uint32_t *sat, size_t sat_stride
     return FOV_OK;
   }
   // Unaligned or 3-byte-pixel sources: the three-kernel reduce / carry / scan path.
-  ctx->sat_layout = std::make_tuple(0, 0, 0, 0, 0);  // it reuses the same scratch bytes
+  ctx->sat_scratch_dirty = true;  // it reuses the same scratch bytes
   FOV_CUDA(ctx,
            launch_sat_encode(ctx->lc(), n, sat, sat_stride, src, src_stride, W, H, linesize,
                              ctx->sat_scratch.base),
@@ -718,8 +767,7 @@ int fov_img_interpolate_logpolar(fov_ctx *ctx, uint8_t *out, int W, int H, int o
   int rc = get_lp_grid(ctx, ow, oh, &grid);
   if (rc) return rc;
   FOV_CUDA(ctx,
-           launch_img_interpolate_logpolar(ctx->lc(), out, W, H, red, ow, oh, cx, cy,
-                                           grid->d_radius, grid->d_dir),
+           launch_img_interpolate_logpolar(ctx->lc(), out, W, H, red, ow, oh, cx, cy, *grid),
            "img interpolate_logpolar launch");
   return FOV_OK;
 }

@@ -56,6 +56,8 @@ struct LogpolarGrid {  // ImageSampler log-polar grid, separable factors
   float *d_cos = nullptr;     // [oh]
   float *d_sin = nullptr;     // [oh]
   double2 *d_dir = nullptr;   // [oh] (cos, sin) of the inverse warp's double-typed angle
+  double *d_radius_f64 = nullptr;  // [ow] radius widened to double (operand of the exact-hit test)
+  double2 *d_lntab = nullptr;      // [kLnExponents * 128] {1 / c, (ow / 20) ln c} (build_logpolar_lntab)
   std::vector<float> h_radius, h_cos, h_sin;
 };
 
@@ -68,11 +70,15 @@ void build_img_grid_axes(int ow, int oh, int W, int H, std::vector<int16_t> &xd,
 void build_logpolar_axes(int ow, int oh, std::vector<float> &radius, std::vector<float> &cs,
                          std::vector<float> &sn);
 void build_logpolar_directions(int oh, std::vector<double2> &dir);
+constexpr int kLnExponents = 31;  // d2 = dx^2 + dy^2 < 2^31 for every accepted geometry
+void build_logpolar_lntab(int ow, std::vector<double2> &tab);
+float logpolar_round_zone(int oh);
 
 // ---- launch context: stream + optional per-kernel event timing ------------------------------
 
 // Per-kernel CUDA-event timing (the analogue of CL_QUEUE_PROFILING_ENABLE, which the reference
 // never switches on, opencl_manager.cc:55).  Off by default: no events are recorded.
+constexpr size_t kMaxPendingEvents = 4096;
 struct Profiler {
   struct Pending {
     const char *name;
@@ -88,6 +94,7 @@ struct Profiler {
   std::map<std::string, Total> totals;
   cudaEvent_t get();
   void collect();  // requires the stream to be idle
+  void recycle();  // folds the pairs that have completed; never waits
   void release();
 };
 
@@ -105,21 +112,28 @@ class KernelScope {
   KernelScope(const LaunchCtx &lc, const char *name) : lc_(lc) {
     if (lc.launches) ++*lc.launches;
     if (lc.prof && lc.prof->enabled) {
+      // a long profiled run must not grow without bound: fold completed pairs now and then
+      if (lc.prof->pending.size() >= kMaxPendingEvents) lc.prof->recycle();
       p_.name = name;
       p_.a = lc.prof->get();
       p_.b = lc.prof->get();
-      cudaEventRecord(p_.a, lc.stream);
-      on_ = true;
+      on_ = p_.a && p_.b && cudaEventRecord(p_.a, lc.stream) == cudaSuccess;
+      if (!on_) give_back();
     }
   }
   ~KernelScope() {
-    if (on_) {
-      cudaEventRecord(p_.b, lc_.stream);
+    if (!on_) return;
+    if (cudaEventRecord(p_.b, lc_.stream) == cudaSuccess)
       lc_.prof->pending.push_back(p_);
-    }
+    else
+      give_back();
   }
 
  private:
+  void give_back() {
+    if (p_.a) lc_.prof->pool.push_back(p_.a);
+    if (p_.b) lc_.prof->pool.push_back(p_.b);
+  }
   const LaunchCtx &lc_;
   Profiler::Pending p_{};
   bool on_ = false;
@@ -175,7 +189,7 @@ cudaError_t launch_img_sample_logpolar(const LaunchCtx &lc, uint8_t *out, int ow
                                        const float *sn, float cx, float cy);
 cudaError_t launch_img_interpolate_logpolar(const LaunchCtx &lc, uint8_t *out, int W, int H,
                                             const uint8_t *red, int ow, int oh, float cx,
-                                            float cy, const float *radius, const double2 *dir);
+                                            float cy, const LogpolarGrid &grid);
 cudaError_t launch_img_logpolar_blur(const LaunchCtx &lc, uint8_t *out, int ow, int oh,
                                      const uint8_t *src);
 cudaError_t launch_img_logpolar_grid_expand(const LaunchCtx &lc, int16_t *grid, int ow, int oh,

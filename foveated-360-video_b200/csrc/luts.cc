@@ -133,6 +133,33 @@ void build_logpolar_directions(int oh, std::vector<double2> &dir) {
   }
 }
 
+// ln table of the log-polar inverse warp: i_f = ow * (log(sqrt(d2)) / 10) (:28-33) = K ln(d2) with
+// K = ow / 20.  One entry per (binary exponent e, top 7 mantissa bits k) of d2: c = the integer of
+// the bin when it holds a single one (every d2 < 256: r = d2 / c - 1 is then exactly 0), else its
+// centre, so that |r| <= 2^-8 and ln(d2) = ln c + r - r^2/2 + r^3/3 - r^4/4 to 5e-14.
+void build_logpolar_lntab(int ow, std::vector<double2> &tab) {
+  const double K = ow / 20.0;
+  tab.resize((size_t)kLnExponents * 128);
+  for (int e = 0; e < kLnExponents; ++e)
+    for (int k = 0; k < 128; ++k) {
+      const double lo = ldexp(1.0 + k / 128.0, e), hi = ldexp(1.0 + (k + 1) / 128.0, e);
+      double c = 0.5 * (lo + hi);
+      if (ceil(hi) - ceil(lo) <= 1.0) c = fmax(ceil(lo), 1.0);  // at most one integer in [lo, hi)
+      tab[(size_t)e * 128 + k].x = 1.0 / c;
+      tab[(size_t)e * 128 + k].y = K * log(c);
+    }
+}
+
+// Half-width of the band around n + 0.5 inside which the single-precision j_f of the inverse
+// log-polar warp may round to the other index than the reference's: both values are within
+// 3e-7 rad of the true angle (float division, atanf, polynomial) times oh / 2 pi, and each is
+// rounded once to the float spacing at "j_f + 2 oh" <= 2.75 oh.
+float logpolar_round_zone(int oh) {
+  const float top = 2.75f * oh;
+  const float quantum = nextafterf(top, INFINITY) - top;
+  return (float)(6e-7 * oh / (2.0 * 3.14159265358979323846)) + quantum;
+}
+
 // Gnomonic viewport constants (projections_program.cl:25-28): (center - 0.5) is promoted to
 // double by the double literals 0.5 / PI and narrowed to float on assignment; sin/cos of the float.
 GnomonicView make_gnomonic_view(float cx, float cy) {

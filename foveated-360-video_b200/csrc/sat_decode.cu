@@ -9,6 +9,7 @@
 #include <cstdlib>
 
 #include "fov360_internal.h"
+#include "pixel_math.cuh"
 #include "projection_common.cuh"
 
 namespace fov {
@@ -95,14 +96,6 @@ struct __align__(16) SampleRow {
                               // 1: the row is sampled at all (:199-200, and j < oh)
                               // 2: its top edge is the bottom edge of the row above
 };
-
-// `.xyz =` store (:212): bytes 0..2 of the target pixel, byte 3 keeps its contents.  Two partial
-// stores (u16 + u8) instead of a read-modify-write of the pixel: the old pixel is never loaded, so
-// no warp waits on the target buffer.
-__device__ __forceinline__ void store_xyz(uint32_t *px, uint32_t rgb) {
-  asm volatile("st.global.u16 [%0], %1;" ::"l"(px), "h"((unsigned short)(rgb & 0xffffu)) : "memory");
-  asm volatile("st.global.u8 [%0+2], %1;" ::"l"(px), "r"((rgb >> 16) & 0xffu) : "memory");
-}
 
 #ifndef FOV360_SAMPLE_MIN_CTAS
 #define FOV360_SAMPLE_MIN_CTAS 6
@@ -282,33 +275,6 @@ __device__ __forceinline__ InterpEntry load_entry(const InterpEntry *p) {
   return e;
 }
 
-// u8 -> float without the conversion pipe: splice the byte into the mantissa of 2^23 (one PRMT)
-// and subtract 2^23 (one FADD); exact for 0..255.
-template <int C>
-__device__ __forceinline__ float byte_to_float(uint32_t v) {
-  return __fsub_rn(__uint_as_float(__byte_perm(v, 0x4B000000u, 0x7440u | C)), 8388608.0f);
-}
-
-// mix(a, b, t) = a + (b - a) * t with every operation rounded separately (no FMA), matching
-// the oracle's scalar float arithmetic (:143-150).
-__device__ __forceinline__ float mix_rn(float a, float b, float t) {
-#ifdef FOV360_FUSED_LERP
-  return __fmaf_rn(__fsub_rn(b, a), t, a);  // <= 1 LSB after truncation, not bit-exact
-#else
-  return __fadd_rn(a, __fmul_rn(__fsub_rn(b, a), t));
-#endif
-}
-
-// trunc(v) for v in [0, 256): the low mantissa bits of v + 2^23 rounded toward zero
-// (convert_uchar3, :150).  Byte 1 of the result is 0, which pack_rgb0 uses as the padding byte.
-__device__ __forceinline__ uint32_t trunc_bits(float v) {
-  return __float_as_uint(__fadd_rz(v, 8388608.0f));
-}
-
-__device__ __forceinline__ uint32_t pack_rgb0(uint32_t c0, uint32_t c1, uint32_t c2) {
-  return __byte_perm(__byte_perm(c0, c1, 0x0040u), c2, 0x5410u);  // c0.b0, c1.b0, c2.b0, 0
-}
-
 constexpr int kInterpPx = 4;         // consecutive pixels per lane: one 16-byte store per row
 // Rows per warp are a template parameter of the kernel (32, 16 or 8): the x-axis work is done once
 // per warp, so large batches want tall tiles, while a single frame is less than one wave of CTAs
@@ -364,50 +330,6 @@ __device__ __forceinline__ uint32_t lerp_px(const float4 v, const float4 d, floa
                    trunc_bits(lerp_rn(v.z, d.z, t)));
 }
 
-// Packed fp32 pairs (sm_100 FMUL2 / FADD2): two independent IEEE single operations per instruction,
-// each rounded exactly like its scalar form.  ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into
-// FFMA2 even though both carry an explicit rounding mode; a multiply with .ftz is never contracted
-// with an add without it, and no operand or product here is subnormal (bytes, ratios k/n, and
-// their differences are 0 or >= 2^-17 in magnitude), so .ftz changes nothing.
-using f32x2 = unsigned long long;
-__device__ __forceinline__ f32x2 pack2(float lo, float hi) {
-  f32x2 r;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
-  return r;
-}
-__device__ __forceinline__ void unpack2(f32x2 v, uint32_t &lo, uint32_t &hi) {
-  asm("mov.b64 {%0, %1}, %2;" : "=r"(lo), "=r"(hi) : "l"(v));
-}
-__device__ __forceinline__ f32x2 mul2_rn(f32x2 a, f32x2 b) {
-  f32x2 r;
-  asm("mul.rn.ftz.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
-  return r;
-}
-__device__ __forceinline__ f32x2 add2_rn(f32x2 a, f32x2 b) {
-  f32x2 r;
-  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
-  return r;
-}
-__device__ __forceinline__ f32x2 sub2_rn(f32x2 a, f32x2 b) {
-  f32x2 r;
-  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
-  return r;
-}
-// both halves: low mantissa bits of v + 2^23 rounded toward zero (trunc_bits)
-__device__ __forceinline__ f32x2 trunc_bits2(f32x2 v) {
-  f32x2 r;
-  asm("add.rz.f32x2 %0, %1, %2;" : "=l"(r) : "l"(v), "l"(0x4B0000004B000000ull));
-  return r;
-}
-// byte C of two pixels as a float pair (byte_to_float twice, one packed subtract)
-template <int C>
-__device__ __forceinline__ f32x2 bytes_to_float2(uint32_t a, uint32_t b) {
-  f32x2 r;
-  asm("mov.b64 %0, {%1, %2};"
-      : "=l"(r)
-      : "r"(__byte_perm(a, 0x4B000000u, 0x7440u | C)), "r"(__byte_perm(b, 0x4B000000u, 0x7440u | C)));
-  return sub2_rn(r, 0x4B0000004B000000ull);
-}
 // lerp_px on a staged column: v = {V.x, V.y | V.z, V.w}, d likewise, t2 = {t, t}.  The .w halves
 // (the exact-hit samples' 4th bytes) ride through the arithmetic unused.
 __device__ __forceinline__ uint32_t lerp_px2(const ulonglong2 v, const ulonglong2 d, f32x2 t2) {
@@ -1016,7 +938,8 @@ cudaError_t launch_sat_interpolate_rect(const LaunchCtx &lc, int n, uint8_t *out
   const size_t px = (size_t)n * W * H;
   static const int force_rows = [] {
     const char *e = getenv("FOV360_INTERP_ROWS");
-    return e ? atoi(e) : 0;
+    const int v = e ? atoi(e) : 0;
+    return (v == 8 || v == 16 || v == 32) ? v : 0;  // the instantiated tile heights
   }();
   const int rows = force_rows ? force_rows : (px < ((size_t)16 << 20) ? 8 : (px < ((size_t)96 << 20) ? 16 : 32));
   const dim3 grid((W + 32 * kInterpPx - 1) / (32 * kInterpPx),

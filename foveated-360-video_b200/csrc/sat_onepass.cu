@@ -35,6 +35,7 @@
 // All sums are plain u32 adds: they wrap mod 2^32 exactly like the reference's `uint currentSum`.
 #include <cstdio>
 #include <cstdlib>
+#include <mutex>
 
 #include "fov360_internal.h"
 #include "sat_common.cuh"
@@ -49,6 +50,7 @@ namespace {
 constexpr int kMaxWarps = 8;
 constexpr int kMaxBandRows = 64;
 constexpr uint32_t kAgg = 1, kInc = 2;  // column-carry states (low 2 bits of a flag word)
+constexpr uint32_t kRow = 3;             // row-carry units: tags of the two kinds never coincide
 
 struct OnePassArgs {
   const uint8_t *src;
@@ -58,7 +60,7 @@ struct OnePassArgs {
   int n, R, nb, ns, nsc;  // frames, band rows, bands, warp strips, CTA strips
   uint32_t epoch, total_tiles;
   uint32_t *counters;  // [0] ticket, [1] finished CTAs
-  uint4 *rowagg;       // [tile][kMaxBandRows]  {r, g, b, epoch}: per-row sums of a CTA tile
+  uint4 *rowagg;       // [tile][kMaxBandRows]  {r, g, b, epoch << 2 | kRow}: per-row sums of a CTA tile
   uint4 *colagg;       // [tile][NW][4][32]     {v0, v1, v2, epoch << 2 | state}: column carry
 #ifdef FOV360_SAT_TRACE
   long long *trace;  // [tile][8] clock64 at the phase boundaries (tools/sat_trace.cu only)
@@ -196,7 +198,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32, MIN_CTAS) sat_onepass_kernel(c
       r0 += v.x, r1 += v.y, r2 += v.z;
     }
     if (s + 1 < a.nsc)  // somebody to the right will want it
-      st_unit(&a.rowagg[(size_t)tile * kMaxBandRows + r], r0, r1, r2, a.epoch);
+      st_unit(&a.rowagg[(size_t)tile * kMaxBandRows + r], r0, r1, r2, (a.epoch << 2) | kRow);
   }
   FOV_TRACE(3);
 
@@ -211,7 +213,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32, MIN_CTAS) sat_onepass_kernel(c
         const int r = lane + 32 * h;
         if (r < rows) {
           uint4 v = ld_unit(pu + r);
-          while (v.w != a.epoch) {
+          while (v.w != ((a.epoch << 2) | kRow)) {
             __nanosleep(20);
             v = ld_unit(pu + r);
           }
@@ -424,6 +426,8 @@ SatOnePassPlan sat_onepass_plan(int n, int W, int H) {
   p.nsc = (p.ns + p.NW - 1) / p.NW;
   static const int band = env_int("FOV360_SAT_BAND_ROWS", 24);
   p.R = band < 1 ? 1 : (band > kMaxBandRows ? kMaxBandRows : band);
+  // one thread per band row publishes the row carries: a forced narrow CTA bounds the band height
+  if (p.R > p.NW * 32) p.R = p.NW * 32;
   p.nb = (H + p.R - 1) / p.R;
   const size_t tiles = (size_t)n * p.nb * p.nsc;
   auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
@@ -431,8 +435,10 @@ SatOnePassPlan sat_onepass_plan(int n, int W, int H) {
   p.off_rowagg = 256;
   p.off_colagg = p.off_rowagg + al(tiles * kMaxBandRows * 16);
   p.bytes = p.off_colagg + al(tiles * p.NW * 128 * 16);
-  // Every carry unit is tagged with the launch epoch, so nothing is cleared between launches of
-  // one layout; the whole scratch is zeroed when the layout changes (stale tags) or the epoch wraps.
+  // Every carry unit is tagged with the launch epoch, which only grows over the life of a context:
+  // a unit left behind by any earlier launch, of this or another tile layout, can never carry the
+  // current tag.  The scratch is zeroed when it is (re)allocated, after the three-kernel fallback
+  // has used the same bytes, and when the epoch wraps.
   p.clear_bytes = p.bytes;
   return p;
 }
@@ -479,11 +485,11 @@ cudaError_t launch_sat_onepass(const LaunchCtx &lc, int n, uint32_t *sat, size_t
   // 3 CTAs of 256 threads per SM bound the registers at 80; the 192-thread CTAs 8K frames use then
   // run 4 per SM.  8 rows in flight per lane while reducing, 4 while scanning.
   auto kernel = sat_onepass_kernel<3, 8, 4>;
-  static bool attr_set[64] = {};
-  if (!attr_set[lc.device & 63]) {
+  // once per device, whichever connection thread gets here first
+  static std::once_flag attr_once[64];
+  std::call_once(attr_once[lc.device & 63], [&] {
     cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
-    attr_set[lc.device & 63] = true;
-  }
+  });
   KernelScope ks(lc, "sat_onepass");
   kernel<<<a.total_tiles, p.NW * 32, smem, lc.stream>>>(a);
   return cudaGetLastError();
