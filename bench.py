@@ -10,8 +10,15 @@ via the C ABI of libfov360.so.
             host->device from pinned memory and its un-warped result device->host inside the
             timed region (video_server.cc:297-299,342-345 are blocking cl::copy; here the copies
             are pipelined over a few contexts = in-order queues)
+  e2e_server  the lane the reference's server runs (video_server.cc:291-345) with the colour
+            conversions on the device: decoded NV12 frame in -> RGB0 -> SAT encode -> sample ->
+            NV12 of the reduced buffer out; only 1.5 B/px up and the reduced buffer down
   roofline  dominant kernel: algorithmic bytes / its CUDA-event duration vs the measured HBM peak
   cpu_baseline  the reference's own kernels (oracle/_ref) or the oracle port on the host cores
+  configs   short runs of the other BASELINE.json configurations (N = 1 only, except serving):
+            4K single frames and batches of 8 over the gaze lattice, the log-polar ImageSampler
+            path beside log-rect at 4K, 8 concurrent 4K streams per GPU (wall clock), and the
+            1080p centre-gaze case the reference's CPU path is quoted on
 
 Multi-GPU (torchrun): frames are independent, every rank runs the same per-GPU batch on its own
 device (weak scaling, no collective on the data path); timing is max over ranks.
@@ -22,8 +29,10 @@ from __future__ import annotations
 
 import argparse
 import ctypes as C
+import hashlib
 import importlib
 import json
+import math
 import os
 import sys
 import threading
@@ -40,11 +49,10 @@ WORKLOADS = {
     "4k": (3840, 1920),
     "8k": (7680, 3840),
 }
+L2_BYTES = 126 << 20
 
 
 def reduced(dim: int) -> int:
-    import math
-
     return 16 * math.ceil(dim / 1.8 / 16)
 
 
@@ -54,6 +62,21 @@ def algorithmic_bytes(W, H, ow, oh):
     sample = 12 * (ow + 1) * (oh + 1) + 4 * ow * oh
     interp = 4 * ow * oh + 4 * W * H
     return {"sat": sat, "sample": sample, "interp": interp, "total": sat + sample + interp}
+
+
+def kernel_bytes_per_frame(W, H, ow, oh):
+    """Algorithmic bytes per FRAME attributed to each kernel."""
+    ab = algorithmic_bytes(W, H, ow, oh)
+    return {
+        "sat_scan": ab["sat"], "sat_onepass": ab["sat"], "sat_reduce": 4 * W * H, "sat_carry": 0,
+        "sat_sample_rect": ab["sample"], "sat_interpolate_rect": ab["interp"],
+        # ImageSampler: 3 useful bytes read + 4 written per reduced pixel; 3x3 stencil reads and
+        # writes the reduced buffer once; the inverse warp reads it once and writes the frame
+        "img_sample_logpolar": 7 * ow * oh, "img_sample_rect": 7 * ow * oh,
+        "img_logpolar_blur": 8 * ow * oh, "img_interpolate_logpolar": 4 * ow * oh + 4 * W * H,
+        # colour conversion: 4 B RGB0 + 1.5 B of planes per pixel of the converted frame
+        "rgb0_to_yuv": 0, "yuv_to_rgb0": 0,
+    }
 
 
 def synth_frame(W, H, seed):
@@ -71,6 +94,27 @@ def gaze_trace(steps, batch, seed=1):
     return np.random.default_rng(seed).random((steps, batch, 2)).astype(np.float32)
 
 
+def gaze_lattice():
+    """9x9 lattice of [0,1]^2 (corners included) + seam cases."""
+    g = [(x / 8.0, y / 8.0) for y in range(9) for x in range(9)]
+    g += [(0.02, 0.5), (0.98, 0.5), (0.02, 0.1), (0.98, 0.9)]
+    return np.asarray(g, np.float32)
+
+
+def gaze_walk(stream: int, frames: int) -> np.ndarray:
+    """smooth random walk, sigma 0.01 per frame, reflected at 0 and 1, seeded by
+    the stream id."""
+    rng = np.random.default_rng(stream)
+    p = rng.random(2)
+    out = np.empty((frames, 2), np.float32)
+    for t in range(frames):
+        p = p + rng.normal(0.0, 0.01, 2)
+        p = np.abs(p)
+        p = 1.0 - np.abs(1.0 - p)
+        out[t] = p
+    return out
+
+
 def peak_hbm_gbs():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     try:
@@ -78,6 +122,48 @@ def peak_hbm_gbs():
             return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     except Exception:
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+_ORIG_AFFINITY = None
+
+
+def restore_affinity():
+    """Undo bind_to_gpu_numa: the CPU legs use every core the process was given."""
+    if _ORIG_AFFINITY is not None:
+        os.sched_setaffinity(0, _ORIG_AFFINITY)
+
+
+def bind_to_gpu_numa(index: int) -> dict:
+    """Pins this process (and therefore the pinned host buffers it allocates afterwards: first
+    touch) to the CPUs local to GPU `index`, when the platform exposes the PCI topology."""
+    info = {"bound": False}
+    try:
+        import pynvml as nv
+
+        nv.nvmlInit()
+        bus = nv.nvmlDeviceGetPciInfo(nv.nvmlDeviceGetHandleByIndex(index)).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        dev = "/sys/bus/pci/devices/" + bus.lower()[-12:]
+        with open(dev + "/numa_node") as fh:
+            info["numa_node"] = int(fh.read().strip())
+        with open(dev + "/local_cpulist") as fh:
+            cpulist = fh.read().strip()
+        cpus = set()
+        for part in cpulist.split(","):
+            if part:
+                lo, _, hi = part.partition("-")
+                cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = os.sched_getaffinity(0)
+        local = cpus & allowed
+        info["local_cpus"], info["allowed_cpus"] = len(local), len(allowed)
+        if local and local != allowed and info["numa_node"] >= 0:
+            global _ORIG_AFFINITY
+            _ORIG_AFFINITY = allowed
+            os.sched_setaffinity(0, local)
+            info["bound"] = True
+    except Exception as exc:  # no NVML / no sysfs topology (virtual machines): nothing to bind to
+        info["note"] = type(exc).__name__
+    return info
 
 
 class ClockSampler(threading.Thread):
@@ -154,28 +240,45 @@ def load_cpu_oracle():
     return orc, kind
 
 
-def cpu_pipeline_once(orc, frame, ow, oh, cx, cy, grid):
-    H, W, _ = frame.shape
-    sat = orc.sat_encode(frame)
-    red = orc.sat_sample_rect(sat, ow, oh, cx, cy, grid=grid)
-    return orc.sat_interpolate_rect(red, W, H, cx, cy)
+class CpuPipeline:
+    """The reference's three stages on the host with every buffer allocated ONCE, like the
+    reference's own frame loop (run_satlogrectilinear.cc:915-949 reuses its cl::Buffers): the
+    timed region holds kernel time only, no 354 MB page-fault storm per 8K frame."""
+
+    def __init__(self, orc, W, H, ow, oh):
+        self.orc, self.W, self.H, self.ow, self.oh = orc, W, H, ow, oh
+        self.grid = orc.sat_create_grid(ow, oh, W, H)
+        self.sat = np.zeros((H, W, 3), np.uint32)
+        self.red = np.zeros((oh, ow, 4), np.uint8)
+        self.full = np.zeros((H, W, 4), np.uint8)
+
+    def __call__(self, frame, cx, cy):
+        o, W, H, ow, oh = self.orc, self.W, self.H, self.ow, self.oh
+        o._sat_encode(self.sat, frame, W, H, W * 4)
+        o._sat_sample_rect(self.red, ow, oh, ow * 4, self.sat, W, H, self.grid, cx, cy)
+        o._sat_interpolate_rect(self.full, W, H, self.red, ow, oh, cx, cy)
+        return self.full
 
 
-def cpu_baseline(W, H, ow, oh, budget_s=12.0, max_frames=64):
+def cpu_baseline(W, H, ow, oh, budget_s=12.0, max_frames=64, centre_only=False):
+    restore_affinity()
     orc, kind = load_cpu_oracle()
     cores = orc.get_threads()
-    frame = synth_frame(W, H, 1)
-    grid = orc.sat_create_grid(ow, oh, W, H)
+    frame = np.ascontiguousarray(synth_frame(W, H, 1))
+    pipe = CpuPipeline(orc, W, H, ow, oh)
     gz = gaze_trace(max_frames + 1, 1, seed=2)[:, 0]
-    cpu_pipeline_once(orc, frame, ow, oh, 0.5, 0.5, grid)  # warm-up (page faults, OpenMP pool)
+    if centre_only:
+        gz[:] = 0.5
+    pipe(frame, 0.5, 0.5)  # warm-up (page faults, OpenMP pool)
     n, t0 = 0, time.perf_counter()
     while n < max_frames and (n == 0 or time.perf_counter() - t0 < budget_s):
-        cpu_pipeline_once(orc, frame, ow, oh, float(gz[n, 0]), float(gz[n, 1]), grid)
+        pipe(frame, float(gz[n, 0]), float(gz[n, 1]))
         n += 1
     dt = time.perf_counter() - t0
     return {"value": n / dt, "unit": "frames/s", "cores": cores, "kind": kind,
             "sample": "%d frame(s) of %dx%d -> %dx%d encode+sample+interpolate in %.1f s, "
-                      "OpenMP over NDRange rows" % (n, W, H, ow, oh, dt)}
+                      "OpenMP over NDRange rows, buffers allocated once, driven from Python "
+                      "(3 ctypes calls per frame)" % (n, W, H, ow, oh, dt)}
 
 
 def run_reference_arm(args, W, H, ow, oh, rank):
@@ -183,19 +286,19 @@ def run_reference_arm(args, W, H, ow, oh, rank):
         return
     orc, kind = load_cpu_oracle()
     cores = orc.get_threads()
-    frame = synth_frame(W, H, 1)
-    grid = orc.sat_create_grid(ow, oh, W, H)
+    frame = np.ascontiguousarray(synth_frame(W, H, 1))
+    pipe = CpuPipeline(orc, W, H, ow, oh)
     gz = gaze_trace(args.steps + args.warmup, 1, seed=1)[:, 0]
     for i in range(args.warmup):
-        cpu_pipeline_once(orc, frame, ow, oh, float(gz[i, 0]), float(gz[i, 1]), grid)
+        pipe(frame, float(gz[i, 0]), float(gz[i, 1]))
     t0 = time.perf_counter()
     for i in range(args.steps):
         j = args.warmup + i
-        cpu_pipeline_once(orc, frame, ow, oh, float(gz[j, 0]), float(gz[j, 1]), grid)
+        pipe(frame, float(gz[j, 0]), float(gz[j, 1]))
     dt = time.perf_counter() - t0
     fps = args.steps / dt
-    sample = "1 frame of %dx%d -> %dx%d per step (bounded sample of the batch), %d host threads" % (
-        W, H, ow, oh, cores)
+    sample = ("1 frame of %dx%d -> %dx%d per step (bounded sample of the batch), %d host threads, "
+              "buffers allocated once" % (W, H, ow, oh, cores))
     line = {
         "impl": "reference", "metric": "frames/s SAT log-rect encode+decode", "value": fps,
         "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
@@ -220,7 +323,53 @@ def pinned_array(m, nbytes):
     return arr, p.value
 
 
+def file_sha16(path):
+    try:
+        with open(path, "rb") as fh:
+            return hashlib.sha256(fh.read()).hexdigest()[:16]
+    except OSError:
+        return None
+
+
+def measured_traffic(workload, batch, kernel):
+    """DRAM bytes per launch of `kernel` from the newest committed `ncu --set full` capture that
+    matches (workload, batch), with a staleness check: every capture records the hash of the
+    source files that define the kernel; a differing hash means the kernel changed since."""
+    best = None
+    for name in ("r02_traffic.json", "r01_traffic.json"):
+        try:
+            with open(os.path.join(ROOT, "profiles", name)) as fh:
+                t = json.load(fh)[workload][str(batch)][kernel]
+        except Exception:
+            continue
+        src = t.get("sources")  # {relative path: sha16 at capture time}
+        if src:
+            stale = any(file_sha16(os.path.join(ROOT, p)) != h for p, h in src.items())
+            state = "stale: kernel source changed since the capture" if stale else "current"
+        else:
+            state = "unverified: capture carries no source hash"
+        best = {"traffic": t["dram_read"] + t["dram_write"],
+                "traffic_source": "profiles/%s <- %s" % (name, t.get("capture")),
+                "traffic_state": state}
+        break
+    return best or {"traffic": None, "traffic_source": None, "traffic_state": "no capture"}
+
+
+def kernel_table(totals, steps, bytes_per_launch, peak):
+    step_ms = sum(v[0] for v in totals.values()) / max(steps, 1)
+    out = {}
+    for name, (tot, cnt) in sorted(totals.items()):
+        per_launch_ms = tot / max(cnt, 1)
+        nbytes = bytes_per_launch.get(name, 0)
+        gbs = nbytes / (per_launch_ms * 1e-3) / 1e9 if per_launch_ms else 0
+        out[name] = {"ms_per_launch": round(per_launch_ms, 4), "launches": cnt,
+                     "share": round(tot / max(steps, 1) / step_ms, 4) if step_ms else 0,
+                     "alg_gbs": round(gbs, 1), "frac": round(gbs / peak, 4)}
+    return out, step_ms
+
+
 def run_gpu_arm(args, W, H, ow, oh, rank, world, local_rank):
+    affinity = bind_to_gpu_numa(local_rank) if not args.no_numa_bind else {"bound": False}
     import torch
 
     fov = importlib.import_module("foveated-360-video_b200")
@@ -292,39 +441,34 @@ def run_gpu_arm(args, W, H, ow, oh, rank, world, local_rank):
     totals = m.profile_totals()
     m.profile(False)
     ab = algorithmic_bytes(W, H, ow, oh)
-    kernel_bytes = {  # algorithmic bytes per FRAME attributed to each kernel
-        "sat_scan": ab["sat"], "sat_onepass": ab["sat"], "sat_reduce": 4 * W * H, "sat_carry": 0,
-        "sat_sample_rect": ab["sample"], "sat_interpolate_rect": ab["interp"],
-    }
     peak, peak_src = peak_hbm_gbs()
-    step_ms = sum(v[0] for v in totals.values()) / K
-    kernels = {}
-    for name, (tot, cnt) in sorted(totals.items()):
-        per_launch_ms = tot / max(cnt, 1)
-        gbs = kernel_bytes.get(name, 0) * B / (per_launch_ms * 1e-3) / 1e9 if per_launch_ms else 0
-        kernels[name] = {"ms_per_launch": round(per_launch_ms, 4), "launches": cnt,
-                         "share": round(tot / K / step_ms, 4), "alg_gbs": round(gbs, 1)}
+    per_frame = kernel_bytes_per_frame(W, H, ow, oh)
+    kernels, _ = kernel_table(totals, K, {k: v * B for k, v in per_frame.items()}, peak)
     dom = max(totals, key=lambda k: totals[k][0])
-    traffic = None
-    try:  # measured DRAM bytes per launch of the dominant kernel, from the committed ncu capture
-        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as fh:
-            t = json.load(fh)[args.workload][str(B)][dom]
-            traffic = t["dram_read"] + t["dram_write"]
-    except Exception:
-        pass
     roofline = {
         "bound": "hbm", "kernel": dom, "achieved": kernels[dom]["alg_gbs"], "peak": peak,
-        "unit": "GB/s", "frac": round(kernels[dom]["alg_gbs"] / peak, 4), "traffic": traffic,
+        "unit": "GB/s", "frac": round(kernels[dom]["alg_gbs"] / peak, 4),
+        **measured_traffic(args.workload, B, dom),
         "peak_source": peak_src,
-        "algorithmic_bytes_per_launch": kernel_bytes.get(dom, 0) * B,
+        "algorithmic_bytes_per_launch": per_frame.get(dom, 0) * B,
         "pipeline": {"bytes_per_frame": ab["total"],
                      "achieved": round(ab["total"] * fps / world / 1e9, 1),
                      "frac": round(ab["total"] * fps / world / 1e9 / peak, 4)},
         "kernels": kernels,
     }
+    for b in (src, sat, red, full):
+        b.free()
 
     # ---- end to end through the C ABI with host buffers ----------------------------------------
     e2e = run_e2e(args, fov, local_rank, W, H, ow, oh, frames, gaze, dist, world)
+    e2e_server = None
+    if not args.no_server_lane:
+        e2e_server = run_server_lane(fov, local_rank, W, H, ow, oh, frames, gaze[Wm:Wm + K], 1,
+                                     min(3, Wm), args.e2e_depth, dist, world)
+
+    configs = None
+    if not args.no_configs:
+        configs = run_configs(args, fov, m, local_rank, rank, world, dist, peak)
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -340,9 +484,14 @@ def run_gpu_arm(args, W, H, ow, oh, rank, world, local_rank):
                        "gaze": "per-frame uniform random [0,1]^2, new every step",
                        "l2": "inputs larger than L2: per step %.0f MB of frames + %.0f MB of SAT "
                              "stream through a 126 MB L2" % (B * fb / 1e6, B * sb / 1e6),
-                       "parallelism": "frames sharded over %d GPU(s), no collective" % world},
+                       "parallelism": "frames sharded over %d GPU(s), no collective" % world,
+                       "host_affinity": affinity},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline,
         }
+        if e2e_server:
+            line["e2e_server"] = e2e_server
+        if configs:
+            line["configs"] = configs
         if cpu:
             line["cpu_baseline"] = cpu
         print(json.dumps(line), flush=True)
@@ -350,6 +499,18 @@ def run_gpu_arm(args, W, H, ow, oh, rank, world, local_rank):
         dist.barrier()
         dist.destroy_process_group()
     m.close()
+
+
+def per_rank_values(value, dist, world):
+    """Every rank's value, in rank order (a sum-reduced one-hot vector; no collective on data)."""
+    if not dist:
+        return [round(float(value), 1)]
+    import torch
+
+    t = torch.zeros(world, dtype=torch.float64, device="cuda")
+    t[dist.get_rank()] = float(value)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return [round(float(v), 1) for v in t.tolist()]
 
 
 def run_e2e(args, fov, device, W, H, ow, oh, frames, gaze, dist, world):
@@ -400,7 +561,9 @@ def run_e2e(args, fov, device, W, H, ow, oh, frames, gaze, dist, world):
     for i in range(K):
         step(Wm + i)
     sync()
-    dt = fov.sharding.reduce_max_seconds(time.perf_counter() - t0, dist, "cuda")
+    local = time.perf_counter() - t0
+    dt = fov.sharding.reduce_max_seconds(local, dist, "cuda")
+    ranks = per_rank_values(B * K / local, dist, world)
     checksum = int(hout[: 4 * W].astype(np.uint32).sum())  # the result really is on the host
     for ln in lanes:
         for k in ("src", "sat", "red", "full"):
@@ -411,7 +574,315 @@ def run_e2e(args, fov, device, W, H, ow, oh, frames, gaze, dist, world):
         ln["m"].close()
     return {"value": world * B * K / dt, "unit": "frames/s", "h2d_bytes_per_step": B * fb,
             "d2h_bytes_per_step": B * fb, "pipeline_depth": depth, "host_checksum": checksum,
+            "per_rank": ranks,
             "timing": "host wall clock around K steps, all streams synchronised on both sides"}
+
+
+def run_server_lane(fov, device, W, H, ow, oh, frames, gaze, group, warm, depth, dist, world,
+                    sync_every_step=False):
+    """The reference server's per-frame lane (video_server.cc:291-345) with the two swscale
+    conversions on the device: the decoded frame arrives as NV12 in pinned host memory (what
+    NVDEC / a software decoder hands over, 1.5 B/px), is copied up, becomes RGB0
+    (fov_nv12_to_rgb0), is SAT-encoded and sampled at the stream's gaze, the reduced buffer becomes
+    NV12 (fov_rgb0_to_nv12: the encoder's input surface) and only that goes back to the host.  The
+    inverse warp is the client's job and is not part of this lane.
+
+    frames: u8 [B][H][W][4] RGB0 (converted to NV12 once, outside the timed region);
+    gaze:   f32 [K][B][2]; jobs of `group` frames go round-robin over `depth` contexts."""
+    B, K = frames.shape[0], gaze.shape[0]
+    fb, sb, rb = 4 * W * H, 12 * W * H, 4 * ow * oh
+    nvb, rnvb = W * H * 3 // 2, ow * oh * 3 // 2
+    njobs = (B + group - 1) // group
+    depth = max(1, min(depth, max(njobs, 2)))  # consecutive jobs (also across steps) alternate lanes
+    lanes = []
+    for _ in range(depth):
+        m = fov.OpenCLManager(device)
+        m.InitializeContext()
+        fov.SATDecoder(m).InitializeGrid(ow, oh, W, H)
+        lane = {"m": m, "conv": fov.VideoFrameConverter(m), "nv": m.Buffer(group * nvb),
+                "src": m.Buffer(group * fb), "sat": m.Buffer(group * sb), "red": m.Buffer(group * rb),
+                "rnv": m.Buffer(group * rnvb)}
+        m.memset(lane["red"], 0, group * rb)
+        lanes.append(lane)
+    m0 = lanes[0]["m"]
+    lib = m0.lib
+    hin, _ = pinned_array(m0, B * nvb)
+    hout, _ = pinned_array(m0, B * rnvb)
+    # NV12 version of every synthetic frame (set-up, untimed): our own converter, checked elsewhere
+    ln = lanes[0]
+    for f in range(B):
+        m0.copy_to_device(ln["src"], frames[f])
+        ln["conv"].RGB0ToNV12(ln["nv"], W, ln["nv"].at(W * H), W, ln["src"], 4 * W, W, H)
+        m0.copy_to_host(hin[f * nvb:(f + 1) * nvb], ln["nv"])
+
+    def step(i):
+        for j in range(njobs):
+            ln = lanes[(i * njobs + j) % depth]
+            m = ln["m"]
+            f0 = j * group
+            n = min(group, B - f0)
+            m._check(lib.fov_memcpy_h2d_async(m.ctx, ln["nv"].ptr, hin.ctypes.data + f0 * nvb, n * nvb))
+            ln["conv"].NV12ToRGB0Frames(n, ln["src"], fb, 4 * W, ln["nv"], nvb, W,
+                                        ln["nv"].at(W * H), nvb, W, W, H)
+            fov.EncodeSampleFramesGPU(m, n, ln["red"], rb, ln["sat"], sb, ln["src"], fb, W, H, 4 * W,
+                                      ow, oh, gaze[i, f0:f0 + n])
+            ln["conv"].RGB0ToNV12Frames(n, ln["rnv"], rnvb, ow, ln["rnv"].at(ow * oh), rnvb, ow,
+                                        ln["red"], rb, 4 * ow, ow, oh)
+            m._check(lib.fov_memcpy_d2h_async(m.ctx, hout.ctypes.data + f0 * rnvb, ln["rnv"].ptr,
+                                              n * rnvb))
+        if sync_every_step:
+            for ln in lanes:
+                ln["m"].Finish()
+
+    def sync():
+        for ln in lanes:
+            ln["m"].Finish()
+        if dist:
+            dist.barrier()
+
+    for i in range(min(warm, K)):
+        step(i)
+    sync()
+    launches0 = sum(ln["m"].launch_count for ln in lanes)
+    t0 = time.perf_counter()
+    for i in range(K):
+        step(i)
+    sync()
+    local = time.perf_counter() - t0
+    launches = sum(ln["m"].launch_count for ln in lanes) - launches0
+    dt = fov.sharding.reduce_max_seconds(local, dist, "cuda")
+    checksum = int(hout[:ow].astype(np.uint32).sum())
+    for ln in lanes:
+        for k in ("nv", "src", "sat", "red", "rnv"):
+            ln[k].free()
+    lib.fov_host_free(m0.ctx, hin.ctypes.data)
+    lib.fov_host_free(m0.ctx, hout.ctypes.data)
+    for ln in lanes:
+        ln["m"].close()
+    return {"value": world * B * K / dt, "unit": "frames/s", "h2d_bytes_per_step": B * nvb,
+            "d2h_bytes_per_step": B * rnvb, "pipeline_depth": depth, "frames_per_call": group,
+            "gpu_launches": launches, "host_checksum": checksum,
+            "per_rank": per_rank_values(B * K / local, dist, world),
+            "stages": "NV12 h2d -> nv12_to_rgb0 -> SAT encode -> sample_rect -> rgb0_to_nv12 -> "
+                      "reduced NV12 d2h (video_server.cc:291-345; the client un-warps)",
+            "timing": "host wall clock around %d steps, every context synchronised %s" % (
+                K, "after every step" if sync_every_step else "on both sides")}
+
+
+# ------------------------------------------------------------------------------------------------
+# The other BASELINE.json configurations (short runs; keys of `configs` in the JSON line)
+# ------------------------------------------------------------------------------------------------
+def ring_depth(footprint):
+    """Distinct buffer sets visited round-robin so that a step never finds its inputs in L2."""
+    return int(min(8, max(2, math.ceil(3 * L2_BYTES / footprint))))
+
+
+def run_logrect_small(fov, m, stream, W, H, B, gazes, reps, peak):
+    """Device-resident encode+sample+interpolate of batches of B frames, one gaze per frame taken
+    from `gazes` in order; CUDA events around the whole run, then a per-kernel pass."""
+    import torch
+
+    ow, oh = reduced(W), reduced(H)
+    fb, sb, rb = 4 * W * H, 12 * W * H, 4 * ow * oh
+    ring = ring_depth(B * (2 * fb + sb + rb))
+    base = synth_frame(W, H, 11)
+    sets = []
+    for r in range(ring):
+        fr = np.stack([np.roll(base, 97 * (r * B + f) + 1, axis=1) for f in range(B)])
+        s = {"src": m.upload(fr), "sat": m.Buffer(B * sb), "red": m.Buffer(B * rb),
+             "full": m.Buffer(B * fb)}
+        m.memset(s["red"], 0, B * rb)
+        sets.append(s)
+    nsteps = (len(gazes) + B - 1) // B
+    gz = np.stack([gazes[np.arange(i * B, i * B + B) % len(gazes)] for i in range(nsteps)])
+
+    def step(i):
+        s = sets[i % ring]
+        fov.FoveateFramesGPU(m, B, s["full"], fb, s["red"], rb, s["sat"], sb, s["src"], fb, W, H,
+                             4 * W, ow, oh, gz[i % nsteps])
+
+    for i in range(3):
+        step(i)
+    m.Finish()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for i in range(nsteps * reps):
+        step(i)
+    e1.record(stream)
+    m.Finish()
+    ms = e0.elapsed_time(e1)
+    m.profile_reset()
+    m.profile(True)
+    for i in range(nsteps):
+        step(i)
+    totals = m.profile_totals()
+    m.profile(False)
+    per_frame = kernel_bytes_per_frame(W, H, ow, oh)
+    kernels, _ = kernel_table(totals, nsteps, {k: v * B for k, v in per_frame.items()}, peak)
+    for s in sets:
+        for b in s.values():
+            b.free()
+    ab = algorithmic_bytes(W, H, ow, oh)
+    fps = B * nsteps * reps / (ms * 1e-3)
+    return {"frames_per_call": B, "gaze_points": int(len(gazes)), "calls_timed": nsteps * reps,
+            "frames_per_s": round(fps, 1), "ms_per_call": round(ms / (nsteps * reps), 4),
+            "pipeline_frac": round(ab["total"] * fps / 1e9 / peak, 4),
+            "l2": "ring of %d buffer sets (%.0f MB each): no step finds its inputs in L2" % (
+                ring, B * (2 * fb + sb + rb) / 1e6),
+            "timing": "CUDA events on the library stream around all calls", "kernels": kernels}
+
+
+def run_logpolar(fov, m, stream, W, H, gazes, reps, peak):
+    """BASELINE configs[3]: ImageSampler log-polar path (sample_logpolar -> blur -> interpolate,
+    image_sampler.cc:577-621, 820-857, 780-818) on single frames over the gaze lattice."""
+    import torch
+
+    ow, oh = reduced(W), reduced(H)
+    fb, rb = 4 * W * H, 4 * ow * oh
+    ring = ring_depth(2 * fb + 2 * rb)
+    base = synth_frame(W, H, 12)
+    img = fov.ImageSampler(m)
+    sets = []
+    for r in range(ring):
+        s = {"src": m.upload(np.roll(base, 131 * r + 1, axis=1)), "red": m.Buffer(rb),
+             "blur": m.Buffer(rb), "full": m.Buffer(fb)}
+        m.memset(s["red"], 0, rb)
+        sets.append(s)
+    n = len(gazes)
+
+    def step(i):
+        s = sets[i % ring]
+        cx, cy = float(gazes[i % n, 0]), float(gazes[i % n, 1])
+        img.SampleFrameLogPolarGPU(s["red"], ow, oh, 4 * ow, s["src"], W, H, 4 * W, cx, cy)
+        img.ApplyLogPolarGaussianBlur(s["blur"], ow, oh, 4 * ow, s["red"])
+        img.InterpolateFrameLogPolarGPU(s["full"], W, H, 4 * W, s["blur"], ow, oh, 4 * ow, cx, cy)
+
+    for i in range(3):
+        step(i)
+    m.Finish()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for i in range(n * reps):
+        step(i)
+    e1.record(stream)
+    m.Finish()
+    ms = e0.elapsed_time(e1)
+    m.profile_reset()
+    m.profile(True)
+    for i in range(n):
+        step(i)
+    totals = m.profile_totals()
+    m.profile(False)
+    kernels, _ = kernel_table(totals, n, kernel_bytes_per_frame(W, H, ow, oh), peak)
+    for s in sets:
+        for b in s.values():
+            b.free()
+    total_bytes = sum(kernel_bytes_per_frame(W, H, ow, oh)[k] for k in
+                      ("img_sample_logpolar", "img_logpolar_blur", "img_interpolate_logpolar"))
+    fps = n * reps / (ms * 1e-3)
+    return {"frames_per_s": round(fps, 1), "ms_per_frame": round(ms / (n * reps), 4),
+            "bytes_per_frame": total_bytes,
+            "pipeline_frac": round(total_bytes * fps / 1e9 / peak, 4),
+            "gaze_points": int(n), "timing": "CUDA events on the library stream around all calls",
+            "kernels": kernels}
+
+
+def run_serving(fov, m, stream, device, W, H, nstreams, nframes, rank, world, dist, peak):
+    """BASELINE configs[4]: `nstreams` concurrent streams on this GPU (64 over 8
+    GPUs, stream s -> GPU s % 8), each with its own random-walk gaze trace; one batched call per
+    frame time.  Wall clock with the host waiting for every frame time (a server delivers each
+    frame before it takes the next), and the server-shaped lane with per-frame PCIe traffic."""
+    ow, oh = reduced(W), reduced(H)
+    fb, sb, rb = 4 * W * H, 12 * W * H, 4 * ow * oh
+    n = nstreams
+    ids = [rank + world * k for k in range(n)]  # the streams that land on this GPU: s % world == rank
+    base = synth_frame(W, H, 13)
+    ring = 3  # distinct frames per stream: consecutive frame times never reuse a frame in L2
+    sets = []
+    for r in range(ring):
+        fr = np.stack([np.roll(base, 131 * s + 517 * r + 1, axis=1) for s in ids])
+        sets.append({"frames": fr, "src": m.upload(fr)})
+    sat, red, full = m.Buffer(n * sb), m.Buffer(n * rb), m.Buffer(n * fb)
+    m.memset(red, 0, n * rb)
+    traces = np.stack([gaze_walk(s, nframes + 3) for s in ids], axis=1)  # [frame][stream][2]
+
+    def frame_time(t):
+        fov.FoveateFramesGPU(m, n, full, fb, red, rb, sat, sb, sets[t % ring]["src"], fb, W, H, 4 * W,
+                             ow, oh, traces[t])
+
+    for t in range(3):
+        frame_time(t)
+    m.Finish()
+    if dist:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for t in range(nframes):
+        frame_time(3 + t)
+        m.Finish()  # the frame time is complete on the device before the next one is issued
+    local = time.perf_counter() - t0
+    synced = fov.sharding.reduce_max_seconds(local, dist, "cuda")
+    if dist:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for t in range(nframes):
+        frame_time(3 + t)
+    m.Finish()
+    local2 = time.perf_counter() - t0
+    queued = fov.sharding.reduce_max_seconds(local2, dist, "cuda")
+    ab = algorithmic_bytes(W, H, ow, oh)
+    out = {
+        "streams_per_gpu": n, "gpus": world, "streams_total": n * world, "frames_per_stream": nframes,
+        "gaze": "per-stream random walk, sigma 0.01 per frame, reflected at 0/1, seed = stream id",
+        "resident": {
+            "frame_time_ms": round(synced / nframes * 1e3, 4),
+            "fps_per_stream": round(nframes / synced, 1),
+            "frames_per_s": round(world * n * nframes / synced, 1),
+            "pipeline_frac": round(ab["total"] * n * nframes / synced / 1e9 / peak, 4),
+            "timing": "host perf_counter, stream synchronised after every frame time, max over ranks",
+            "frames_per_s_queued": round(world * n * nframes / queued, 1),
+        },
+    }
+    frames0 = sets[0]["frames"]
+    for s in sets:
+        s["src"].free()
+    for b in (sat, red, full):
+        b.free()
+    out["server_lane"] = run_server_lane(fov, device, W, H, ow, oh, frames0, traces[3:3 + nframes],
+                                         n, 3, 2, dist, world)
+    return out
+
+
+def run_configs(args, fov, m, device, rank, world, dist, peak):
+    import torch
+
+    stream = torch.cuda.ExternalStream(m.stream, device=device)
+    out = {}
+    W4, H4 = WORKLOADS["4k"]
+    if world == 1:
+        lat = gaze_lattice()
+        # BASELINE configs[1]: 4K at varying gaze points, single frames and batches of 8
+        out["4k_gaze_sweep_single"] = run_logrect_small(fov, m, stream, W4, H4, 1, lat, 3, peak)
+        out["4k_gaze_sweep_batch8"] = run_logrect_small(fov, m, stream, W4, H4, 8, lat, 3, peak)
+        W8, H8 = WORKLOADS["8k"]
+        out["8k_single_frame"] = run_logrect_small(fov, m, stream, W8, H8, 1, lat[::4], 3, peak)
+        # BASELINE configs[3]: log-polar ImageSampler path beside log-rect, 4K single frames
+        lp = run_logpolar(fov, m, stream, W4, H4, lat, 3, peak)
+        lp["logrect_ms_per_frame"] = out["4k_gaze_sweep_single"]["ms_per_call"]
+        lp["logpolar_over_logrect_time"] = round(
+            lp["ms_per_frame"] / out["4k_gaze_sweep_single"]["ms_per_call"], 3)
+        out["4k_logpolar_vs_logrect"] = lp
+        # BASELINE configs[0]: 1080p, fixed centre gaze - the case the reference's CPU path runs
+        W1, H1 = WORKLOADS["1080p"]
+        centre = np.asarray([(0.5, 0.5)], np.float32)
+        c0 = run_logrect_small(fov, m, stream, W1, H1, 1, centre, 60, peak)
+        if not args.no_cpu_baseline:
+            c0["cpu_reference"] = cpu_baseline(W1, H1, reduced(W1), reduced(H1), budget_s=3.0,
+                                               max_frames=32, centre_only=True)
+        out["1080p_centre_gaze"] = c0
+    # BASELINE configs[4]: 64 concurrent 4K streams over 8 GPUs = 8 per GPU
+    out["serving_4k_streams"] = run_serving(fov, m, stream, device, W4, H4, 8, args.serve_frames,
+                                            rank, world, dist, peak)
+    return out
 
 
 def main():
@@ -424,7 +895,11 @@ def main():
     ap.add_argument("--batch", type=int, default=16,
                     help="frames per step per GPU (SURVEY 8(d): cfg3 is a batch of 16 frames)")
     ap.add_argument("--e2e-depth", type=int, default=6)
+    ap.add_argument("--serve-frames", type=int, default=120)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="headline only")
+    ap.add_argument("--no-server-lane", action="store_true")
+    ap.add_argument("--no-numa-bind", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     W, H = WORKLOADS[args.workload]

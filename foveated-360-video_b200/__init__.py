@@ -10,6 +10,7 @@ from . import sharding  # noqa: F401
 from ._capi import PROTOTYPES, header_symbols, library_path, load  # noqa: F401
 from .host import (  # noqa: F401
     DeviceBuffer,
+    EncodeSampleFramesGPU,
     FoveateFramesGPU,
     FovError,
     GazeViewPoints,

@@ -50,6 +50,8 @@ PROTOTYPES = {
     "fov_sat_decode": (_i, [_vp, _vp, _i, _vp, _i, _i]),
     "fov_sat_foveate_batched": (_i, [_vp, _i, _vp, _sz, _vp, _sz, _vp, _sz, _vp, _sz,
                                      _i, _i, _i, _i, _i, _fp]),
+    "fov_sat_encode_sample_batched": (_i, [_vp, _i, _vp, _sz, _vp, _sz, _vp, _sz,
+                                           _i, _i, _i, _i, _i, _fp]),
     "fov_img_grid_init": (_i, [_vp, _i, _i, _i, _i]),
     "fov_img_grid_export": (_i, [_vp, _vp, _i, _i, _i, _i]),
     "fov_img_sample_rect": (_i, [_vp, _vp, _i, _i, _i, _vp, _i, _i, _i, _f, _f]),

@@ -603,18 +603,26 @@ int fov_sat_decode(fov_ctx *ctx, uint8_t *out, int out_linesize, const uint32_t 
   return FOV_OK;
 }
 
-int fov_sat_foveate_batched(fov_ctx *ctx, int n, uint8_t *full_out, size_t full_stride,
-                            uint8_t *reduced, size_t red_stride, uint32_t *sat, size_t sat_stride,
-                            const uint8_t *src, size_t src_stride, int W, int H, int linesize,
-                            int ow, int oh, const float *gaze_xy) {
+int fov_sat_encode_sample_batched(fov_ctx *ctx, int n, uint8_t *reduced, size_t red_stride,
+                                  uint32_t *sat, size_t sat_stride, const uint8_t *src,
+                                  size_t src_stride, int W, int H, int linesize, int ow, int oh,
+                                  const float *gaze_xy) {
   int rc = fov_sat_encode_batched(ctx, n, sat, sat_stride, src, src_stride, W, H, linesize);
   if (rc) return rc;
   // RGB0 frames with 4-byte aligned rows let sample_rect read its 1x1 boxes from the frame
   static const bool no_hint = getenv("FOV360_SAMPLE_NO_SRC") != nullptr;
   const bool hint = !no_hint && linesize / W == 4 && (linesize % 4) == 0 && ((uintptr_t)src % 4) == 0 &&
                     (src_stride % 4) == 0;
-  rc = sample_rect_batched(ctx, n, reduced, red_stride, ow, oh, 4 * ow, sat, sat_stride, W, H,
-                           gaze_xy, hint ? src : nullptr, src_stride, linesize);
+  return sample_rect_batched(ctx, n, reduced, red_stride, ow, oh, 4 * ow, sat, sat_stride, W, H,
+                             gaze_xy, hint ? src : nullptr, src_stride, linesize);
+}
+
+int fov_sat_foveate_batched(fov_ctx *ctx, int n, uint8_t *full_out, size_t full_stride,
+                            uint8_t *reduced, size_t red_stride, uint32_t *sat, size_t sat_stride,
+                            const uint8_t *src, size_t src_stride, int W, int H, int linesize,
+                            int ow, int oh, const float *gaze_xy) {
+  int rc = fov_sat_encode_sample_batched(ctx, n, reduced, red_stride, sat, sat_stride, src,
+                                         src_stride, W, H, linesize, ow, oh, gaze_xy);
   if (rc) return rc;
   return fov_sat_interpolate_rect_batched(ctx, n, full_out, full_stride, W, H, reduced, red_stride,
                                           ow, oh, gaze_xy);

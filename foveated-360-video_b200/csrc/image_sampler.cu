@@ -85,6 +85,16 @@ __device__ __forceinline__ int logpolar_delta(float radius, float trig) {
   return (int)(int16_t)__float2int_rz(__fmul_rn(radius, trig));
 }
 
+// v % w as C evaluates it (the sign of the dividend for negative v), for 0 < w < 2^15 and
+// |v| < 2^22: a float estimate of the quotient, corrected by at most one either way.
+__device__ __forceinline__ int mod_width(int v, int w, float rcp_w) {
+  if (v < 0) return v % w;  // only reachable for frames narrower than 3277 pixels
+  int r = v - __float2int_rz(__fmul_rn((float)v, rcp_w)) * w;
+  if (r < 0) r += w;
+  if (r >= w) r -= w;
+  return r;
+}
+
 __global__ void __launch_bounds__(256) img_sample_logpolar_kernel(
     const GatherArgs a, const float *__restrict__ radius, const float *__restrict__ cs,
     const float *__restrict__ sn) {
@@ -93,6 +103,7 @@ __global__ void __launch_bounds__(256) img_sample_logpolar_kernel(
   if (i >= a.ow || j0 >= a.oh) return;
   const float r = radius[i];
   const int W10 = 10 * a.W;
+  const float rcpW = __frcp_rn((float)a.W);
   uint8_t *ocol = a.out + (size_t)i * a.obpp;
   const uint8_t *sp[kGatherRows];
   bool on[kGatherRows];
@@ -101,7 +112,7 @@ __global__ void __launch_bounds__(256) img_sample_logpolar_kernel(
     const int j = min(j0 + k, a.oh - 1);
     int x = gaze_plus(a.cx, a.W, logpolar_delta(r, cs[j]));
     int y = gaze_plus(a.cy, a.H, logpolar_delta(r, sn[j]));
-    x = (x + W10) % a.W;  // :73
+    x = mod_width(x + W10, a.W, rcpW);  // :73
     y = clampi(y, 0, a.H - 1);
     on[k] = j0 + k < a.oh && x >= 0;  // :76-77 (x stays negative only for x < -10 W)
     sp[k] = a.src + (size_t)y * a.src_linesize + (size_t)max(x, 0) * a.sbpp;
@@ -247,6 +258,7 @@ __global__ void __launch_bounds__(kLpThreads, 4) img_interpolate_logpolar_kernel
   const float base_up = __fadd_rn(base_x, ohq), base_dn = __fsub_rn(base_x, ohq);
   uint32_t *op = a.out + (size_t)y0 * W + xx;
   const uint32_t magic = a.magic;
+  const float ow_top = (float)(ow - 1);
 
   for (int r0 = 0; r0 < nrows; r0 += 2, op += 2 * (size_t)W) {
     float i_f[2], j_f[2], tt[2], aa[2];
@@ -266,7 +278,9 @@ __global__ void __launch_bounds__(kLpThreads, 4) img_interpolate_logpolar_kernel
       double q = fma(rr, a.k3, a.k2);
       q = fma(rr, q, a.k1);
       q = fma(rr, q, a.k0);
-      i_f[k] = (float)fma(rr, q, te.y);
+      // clamp(round / floor / ceil(i_f), 0, ow - 1) (:34, :59, :61) = the same of min(i_f, ow - 1):
+      // i_f >= 0, and beyond ow - 1 all three indices are ow - 1 whatever the ratio
+      i_f[k] = fminf((float)fma(rr, q, te.y), ow_top);
       // ---- octant reduction of the angle ----
       swp[k] = rw.ady > adx;
       neg[k] = (rw.dy < 0) != negx;
@@ -304,10 +318,10 @@ __global__ void __launch_bounds__(kLpThreads, 4) img_interpolate_logpolar_kernel
       const float fi = floorf(i_f[k]);
       ir[k] = __fsub_rn(i_f[k], fi);
       int ii = __float2int_rz(fi);
-      int i = min(ii + (ir[k] >= 0.5f ? 1 : 0), ow - 1);  // :34 (i_f >= 0)
+      int i = ii + (ir[k] >= 0.5f ? 1 : 0);  // :34
       if (fabsf(jr[k] - 0.5f) < a.zone || centre[k]) {
         // round(j_f) is not certain: it matters only if a candidate is an exact hit
-        const bool ha = logpolar_hits(a, i, min(jj, oh - 1), cxw, cyh, x, yy[k]);
+        const bool ha = logpolar_hits(a, i, jj, cxw, cyh, x, yy[k]);  // j_f < oh
         const bool hb = logpolar_hits(a, i, min(jj + 1, oh - 1), cxw, cyh, x, yy[k]);
         if (ha || hb || centre[k]) {
           if (centre[k]) ir[k] = 0.0f, ii = 0, i = 0;  // i_f = 0 at the gaze pixel itself (:28-29)
@@ -318,8 +332,8 @@ __global__ void __launch_bounds__(kLpThreads, 4) img_interpolate_logpolar_kernel
       }
       const int j = min(jj + (jr[k] >= 0.5f ? 1 : 0), oh - 1);  // :44
       hit[k] = logpolar_hits(a, i, j, cxw, cyh, x, yy[k]);
-      const int min_i = min(ii, ow - 1);                            // :59
-      const int max_i = min(ii + (ir[k] > 0.0f ? 1 : 0), ow - 1);   // :61
+      const int min_i = ii;                             // :59
+      const int max_i = ii + (ir[k] > 0.0f ? 1 : 0);    // :61
       const int jn = jj + (jr[k] > 0.0f ? 1 : 0);                   // :60, :62: j_f + oh is exact
       ti0[k] = hit[k] ? i : min_i;
       ti1[k] = hit[k] ? i : max_i;
@@ -402,7 +416,8 @@ __global__ void __launch_bounds__(256) img_logpolar_blur_kernel(uint32_t *__rest
 // vertically first (top + bottom of a column is shared by three output pixels); only the three
 // weighted products and their two sums (:123-136) are float operations, rounded one by one like the
 // reference's.
-constexpr int kBlurRows = 16;  // rows per warp
+constexpr int kBlurRows = 8;   // rows per warp
+constexpr int kBlurChunk = 4;  // rows requested together
 constexpr int kBlurWarps = 4;
 
 struct BlurCol {  // one row of the window: 6 columns (left halo, 4 own, right halo)
@@ -422,7 +437,7 @@ __device__ __forceinline__ float half_hi_to_float(uint32_t v) {
   return __fsub_rn(__uint_as_float(__byte_perm(v, 0x4B000000u, 0x7632u)), 8388608.0f);
 }
 
-__global__ void __launch_bounds__(32 * kBlurWarps) img_logpolar_blur4_kernel(
+__global__ void __launch_bounds__(32 * kBlurWarps, 6) img_logpolar_blur4_kernel(
     uint4 *__restrict__ out, int ow, int oh, const uint32_t *__restrict__ src) {
   const int lane = threadIdx.x, warp = threadIdx.y;
   const int ow4 = ow >> 2;
@@ -444,57 +459,67 @@ __global__ void __launch_bounds__(32 * kBlurWarps) img_logpolar_blur4_kernel(
   const float P1 = 0.3377, P2 = 0.1217, P3 = 0.0439;  // :111
   const bool first = lane == 0, last = lane == 31 || gc == ow4 - 1;
   const int il = max(i0 - 1, 0), irr = min(i0 + 4, ow - 1);  // clamp-to-edge halo columns (:112-121)
-  uint4 raw_mid = make_uint4(0, 0, 0, 0);
-  auto load_row = [&](int j, BlurCol &c, uint4 &raw) {
-    const uint32_t *row = src + (size_t)j * ow;
-    raw = __ldg(reinterpret_cast<const uint4 *>(row) + gc);
-    uint32_t left = __shfl_up_sync(0xffffffffu, raw.w, 1);
-    uint32_t right = __shfl_down_sync(0xffffffffu, raw.x, 1);
-    if (first) left = __ldg(row + il);
-    if (last) right = __ldg(row + irr);
-    blur_split(c, 0, left);
-    blur_split(c, 1, raw.x);
-    blur_split(c, 2, raw.y);
-    blur_split(c, 3, raw.z);
-    blur_split(c, 4, raw.w);
-    blur_split(c, 5, right);
+  struct Raw6 {
+    uint32_t p[6];  // left halo, the lane's 4 pixels, right halo
   };
-  BlurCol top, mid, bot;
-  uint4 raw_tmp;
-  load_row(max(j0 - 1, 0), top, raw_tmp);
-  load_row(j0, mid, raw_mid);
-  for (int r = 0; r < nrows; ++r, orow += ow4) {
-    uint4 raw_bot;
-    load_row(min(j0 + r + 1, oh - 1), bot, raw_bot);
-    uint32_t vrb[6], vg[6];
+  auto load_row = [&](int j) {
+    const uint32_t *row = src + (size_t)j * ow;
+    const uint4 raw = __ldg(reinterpret_cast<const uint4 *>(row) + gc);
+    Raw6 r;
+    r.p[0] = __shfl_up_sync(0xffffffffu, raw.w, 1);
+    r.p[5] = __shfl_down_sync(0xffffffffu, raw.x, 1);
+    if (first) r.p[0] = __ldg(row + il);
+    if (last) r.p[5] = __ldg(row + irr);
+    r.p[1] = raw.x, r.p[2] = raw.y, r.p[3] = raw.z, r.p[4] = raw.w;
+    return r;
+  };
+  auto split = [](const Raw6 &r) {
+    BlurCol c;
 #pragma unroll
-    for (int k = 0; k < 6; ++k) {
-      vrb[k] = top.rb[k] + bot.rb[k];
-      vg[k] = top.g[k] + bot.g[k];
-    }
-    uint32_t px[4];
-    const uint32_t centre[4] = {raw_mid.x, raw_mid.y, raw_mid.z, raw_mid.w};
+    for (int k = 0; k < 6; ++k) blur_split(c, k, r.p[k]);
+    return c;
+  };
+  BlurCol top = split(load_row(max(j0 - 1, 0)));
+  Raw6 raw_mid = load_row(j0);
+  BlurCol mid = split(raw_mid);
+  for (int r0 = 0; r0 < nrows; r0 += kBlurChunk) {
+    // the next kBlurChunk rows are requested before any of them is used
+    Raw6 nxt[kBlurChunk];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const uint32_t crb = vrb[k] + vrb[k + 2], cg = vg[k] + vg[k + 2];                  // corners
-      const uint32_t erb = vrb[k + 1] + mid.rb[k] + mid.rb[k + 2];                       // edges
-      const uint32_t eg = vg[k + 1] + mid.g[k] + mid.g[k + 2];
-      const float s0 = __fadd_rn(__fadd_rn(__fmul_rn(P3, half_lo_to_float(crb)),
-                                           __fmul_rn(P2, half_lo_to_float(erb))),
-                                 __fmul_rn(P1, byte_to_float<0>(centre[k])));
-      const float s1 = __fadd_rn(__fadd_rn(__fmul_rn(P3, half_lo_to_float(cg)),
-                                           __fmul_rn(P2, half_lo_to_float(eg))),
-                                 __fmul_rn(P1, byte_to_float<1>(centre[k])));
-      const float s2 = __fadd_rn(__fadd_rn(__fmul_rn(P3, half_hi_to_float(crb)),
-                                           __fmul_rn(P2, half_hi_to_float(erb))),
-                                 __fmul_rn(P1, byte_to_float<2>(centre[k])));
-      const uint32_t blurred = pack_rgb0(trunc_bits(s0), trunc_bits(s1), trunc_bits(s2));
-      px[k] = i0 + k < half ? centre[k] : blurred;  // :138-139
+    for (int c = 0; c < kBlurChunk; ++c) nxt[c] = load_row(min(j0 + r0 + c + 1, oh - 1));
+#pragma unroll
+    for (int c = 0; c < kBlurChunk; ++c, orow += ow4) {
+      const BlurCol bot = split(nxt[c]);
+      uint32_t vrb[6], vg[6];
+#pragma unroll
+      for (int k = 0; k < 6; ++k) {
+        vrb[k] = top.rb[k] + bot.rb[k];
+        vg[k] = top.g[k] + bot.g[k];
+      }
+      uint32_t px[4];
+      const uint32_t centre[4] = {raw_mid.p[1], raw_mid.p[2], raw_mid.p[3], raw_mid.p[4]};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const uint32_t crb = vrb[k] + vrb[k + 2], cg = vg[k] + vg[k + 2];  // corners
+        const uint32_t erb = vrb[k + 1] + mid.rb[k] + mid.rb[k + 2];       // edges
+        const uint32_t eg = vg[k + 1] + mid.g[k] + mid.g[k + 2];
+        const float s0 = __fadd_rn(__fadd_rn(__fmul_rn(P3, half_lo_to_float(crb)),
+                                             __fmul_rn(P2, half_lo_to_float(erb))),
+                                   __fmul_rn(P1, byte_to_float<0>(centre[k])));
+        const float s1 = __fadd_rn(__fadd_rn(__fmul_rn(P3, half_lo_to_float(cg)),
+                                             __fmul_rn(P2, half_lo_to_float(eg))),
+                                   __fmul_rn(P1, byte_to_float<1>(centre[k])));
+        const float s2 = __fadd_rn(__fadd_rn(__fmul_rn(P3, half_hi_to_float(crb)),
+                                             __fmul_rn(P2, half_hi_to_float(erb))),
+                                   __fmul_rn(P1, byte_to_float<2>(centre[k])));
+        const uint32_t blurred = pack_rgb0(trunc_bits(s0), trunc_bits(s1), trunc_bits(s2));
+        px[k] = i0 + k < half ? centre[k] : blurred;  // :138-139
+      }
+      if (active && r0 + c < nrows) __stcs(orow, make_uint4(px[0], px[1], px[2], px[3]));
+      top = mid;
+      mid = bot;
+      raw_mid = nxt[c];
     }
-    if (active) __stcs(orow, make_uint4(px[0], px[1], px[2], px[3]));
-    top = mid;
-    mid = bot;
-    raw_mid = raw_bot;
   }
 }
 

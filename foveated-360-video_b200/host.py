@@ -247,6 +247,17 @@ def FoveateFramesGPU(m: OpenCLManager, n, full_out, full_stride, reduced, reduce
         g.ctypes.data_as(C.POINTER(C.c_float))))
 
 
+def EncodeSampleFramesGPU(m: OpenCLManager, n, reduced, reduced_stride, sat, sat_stride, source,
+                          source_stride, width, height, source_linesize, ow, oh, gaze):
+    """video_server.cc:300-338 (encode -> sample; the client un-warps) for n frames / streams."""
+    g = _gaze_array(gaze)
+    assert g.shape[0] == n
+    m._check(m.lib.fov_sat_encode_sample_batched(
+        m.ctx, n, _ptr(reduced), reduced_stride, _ptr(sat), sat_stride, _ptr(source),
+        source_stride, width, height, source_linesize, ow, oh,
+        g.ctypes.data_as(C.POINTER(C.c_float))))
+
+
 class ImageSampler:
     """image_sampler.h:29-102 (no-SAT baseline: log-rect point sampling and log-polar)."""
 

@@ -158,6 +158,16 @@ int fov_sat_foveate_batched(fov_ctx *ctx, int n, uint8_t *full_out, size_t full_
                             const uint8_t *src, size_t src_stride, int src_width, int src_height,
                             int src_linesize, int red_width, int red_height, const float *gaze_xy);
 
+/* The server's per-frame sequence (video_server.cc:300-338: EncodeFrameGPU ->
+ * SampleFrameRectGPU; the inverse warp runs on the client) for n independent frames / streams
+ * with per-frame gaze.  Same layout rules as fov_sat_foveate_batched, of which this is the first
+ * two stages. */
+int fov_sat_encode_sample_batched(fov_ctx *ctx, int n, uint8_t *reduced, size_t red_stride,
+                                  uint32_t *sat, size_t sat_stride, const uint8_t *src,
+                                  size_t src_stride, int src_width, int src_height,
+                                  int src_linesize, int red_width, int red_height,
+                                  const float *gaze_xy);
+
 /* ---- ImageSampler (image_sampler.h:57-65, 74-78, 84-91) --------------------------------- */
 
 /* ImageSampler::InitializeGrid (image_sampler.cc:170-202; create_grid_kernel,
