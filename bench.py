@@ -858,6 +858,9 @@ def run_configs(args, fov, m, device, rank, world, dist, peak):
     stream = torch.cuda.ExternalStream(m.stream, device=device)
     out = {}
     W4, H4 = WORKLOADS["4k"]
+    # BASELINE configs[4]: 64 concurrent 4K streams over 8 GPUs = 8 per GPU
+    out["serving_4k_streams"] = run_serving(fov, m, stream, device, W4, H4, 8, args.serve_frames,
+                                            rank, world, dist, peak)
     if world == 1:
         lat = gaze_lattice()
         # BASELINE configs[1]: 4K at varying gaze points, single frames and batches of 8
@@ -879,9 +882,6 @@ def run_configs(args, fov, m, device, rank, world, dist, peak):
             c0["cpu_reference"] = cpu_baseline(W1, H1, reduced(W1), reduced(H1), budget_s=3.0,
                                                max_frames=32, centre_only=True)
         out["1080p_centre_gaze"] = c0
-    # BASELINE configs[4]: 64 concurrent 4K streams over 8 GPUs = 8 per GPU
-    out["serving_4k_streams"] = run_serving(fov, m, stream, device, W4, H4, 8, args.serve_frames,
-                                            rank, world, dist, peak)
     return out
 
 

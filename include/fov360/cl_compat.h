@@ -73,6 +73,9 @@ class Buffer {
       std::cerr << "cl::Buffer: " << fov_last_error_string(context()) << std::endl;
       block_->ptr = nullptr;
     }
+#ifdef FOV360_ZERO_NEW_BUFFERS  // deterministic contents for hash-based checks (OpenCL leaves them undefined)
+    if (rc == FOV_OK) fov_memset(context(), block_->ptr, 0, size);
+#endif
     if (err) *err = rc;
   }
   cl_mem operator()() const { return block_ ? block_->ptr : nullptr; }

@@ -5,6 +5,8 @@ Tolerances: SAT, grids, sample_rect, decode, ImageSampler gathers - BIT-EXACT.
 interpolate_rect, blur - <= 1 LSB per channel (BASELINE.json north_star); in practice they are
 bit-exact too and the tests report the mismatch count.  interpolate_logpolar - <= 1 LSB on
 >= 99.9 % of pixels (index rounding at round()/floor() boundaries)."""
+import os
+
 import numpy as np
 import pytest
 
@@ -99,7 +101,7 @@ def test_small_golden_vectors(dev, small):
         got = dev.m.copy_to_host(np.empty((H, W, 4), np.uint8), it)
         diff = np.abs(got[..., :3].astype(np.int16) -
                       small["interp_logpolar_%d" % k][..., :3].astype(np.int16)).max(axis=2)
-        assert (diff > 1).mean() <= 1e-3, (k, int((diff > 1).sum()))
+        assert int((diff > 1).sum()) == 0, (k, int((diff > 1).sum()))
 
 
 @pytest.mark.parametrize("idx", [0, 1, 2])
@@ -547,7 +549,66 @@ def test_image_sampler_vs_oracle(dev, oracle, W, H, ow, oh):
         want = oracle.img_interpolate_logpolar(lp, W, H, cx, cy)
         diff = np.abs(got[..., :3].astype(np.int16) - want[..., :3].astype(np.int16)).max(axis=2)
         bad = int((diff > 1).sum())
-        assert bad <= 1e-3 * W * H, (cx, cy, bad)
+        assert bad == 0, (cx, cy, bad)  # contract: <= 1 LSB on >= 99.9 %; held on every pixel
+
+
+# --------------------------------------------------------- directly against the reference ----
+@pytest.mark.skipif(not O.ref_available(), reason="oracle/_ref/libfovref.so not present")
+def test_8k_frame_against_reference_library(dev):
+    """One full-size 8K frame, device results compared DIRECTLY with oracle/_ref (the reference's own
+    .cl kernels compiled by oracle/build_oracle.py; the library travels to the GPU box), not through
+    the restatement: SAT, reduced buffer (untouched-pixel semantics included) and un-warped frame at
+    the centre and at a seam gaze."""
+    ref = O.Oracle("ref")
+    ref.set_threads(len(os.sched_getaffinity(0)))
+    W, H = 7680, 3840
+    ow, oh = O.reduced_size(W), O.reduced_size(H)
+    frame = O.lcg_frame(W, H, 2024)
+    sat, sat_buf = dev.sat(frame)
+    want_sat = ref.sat_encode(frame)
+    assert np.array_equal(sat, want_sat)
+    del sat
+    grid = ref.sat_create_grid(ow, oh, W, H)
+    assert np.array_equal(dev.dec.ExportGrid(ow, oh, W, H), grid)
+    for cx, cy in [(0.5, 0.5), (0.98, 0.9)]:
+        red, _ = dev.sample(sat_buf, W, H, ow, oh, cx, cy, prefill=0xAB)
+        want_red = ref.sat_sample_rect(want_sat, ow, oh, cx, cy, grid=grid, out=ab(oh, ow))
+        assert np.array_equal(red, want_red), (cx, cy)
+        full = dev.interpolate(red, W, H, cx, cy)
+        want_full = ref.sat_interpolate_rect(want_red, W, H, cx, cy)
+        assert max_lsb(full[..., :3], want_full[..., :3]) <= INTERP_TOL, (cx, cy)
+        assert np.array_equal(full, want_full), (cx, cy)  # the 4th byte too
+
+
+@pytest.mark.skipif(not O.ref_available(), reason="oracle/_ref/libfovref.so not present")
+def test_logpolar_path_against_reference_library(dev):
+    """ImageSampler log-polar path at 4K directly against oracle/_ref: gathers and blur bit-exact,
+    the inverse warp within 1 LSB on EVERY pixel (the contract asks for 99.9 %), and the share of
+    bit-identical pixels reported."""
+    ref = O.Oracle("ref")
+    ref.set_threads(len(os.sched_getaffinity(0)))
+    W, H = 3840, 1920
+    ow, oh = O.reduced_size(W), O.reduced_size(H)
+    frame = O.lcg_frame(W, H, 99)
+    src = dev.m.upload(frame)
+    for cx, cy in [(0.5, 0.5), (0.02, 0.3), (1.0, 1.0)]:
+        red = dev.m.upload(ab(oh, ow))
+        dev.img.SampleFrameLogPolarGPU(red, ow, oh, 4 * ow, src, W, H, 4 * W, cx, cy)
+        lp = dev.m.copy_to_host(ab(oh, ow), red)
+        assert np.array_equal(lp, ref.img_sample_logpolar(frame, ow, oh, cx, cy, out=ab(oh, ow)))
+        bl = dev.m.Buffer(4 * ow * oh)
+        dev.img.ApplyLogPolarGaussianBlur(bl, ow, oh, 4 * ow, red)
+        assert np.array_equal(dev.m.copy_to_host(ab(oh, ow), bl), ref.img_logpolar_blur(lp))
+        it = dev.m.Buffer(4 * W * H)
+        dev.img.InterpolateFrameLogPolarGPU(it, W, H, 4 * W, red, ow, oh, 4 * ow, cx, cy)
+        got = dev.m.copy_to_host(np.empty((H, W, 4), np.uint8), it)
+        want = ref.img_interpolate_logpolar(lp, W, H, cx, cy)
+        diff = np.abs(got[..., :3].astype(np.int16) - want[..., :3].astype(np.int16)).max(axis=2)
+        assert int(diff.max()) <= 1, (cx, cy, int((diff > 1).sum()))
+        assert (diff == 0).mean() >= 0.99, (cx, cy, float((diff == 0).mean()))
+        for b in (red, bl, it):
+            b.free()
+    src.free()
 
 
 # ------------------------------------------------------------------------------- plumbing ----

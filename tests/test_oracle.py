@@ -1,6 +1,8 @@
 """CPU tests of the oracle (oracle/fov_oracle.c): pinned to the golden fixtures generated from the
 reference's own kernel sources, to the reference library itself when it is present, and to the
 invariants SURVEY.md section 4 derives from the reference code."""
+import os
+
 import numpy as np
 import pytest
 
@@ -100,6 +102,36 @@ def test_port_matches_reference_library_bit_for_bit():
             assert np.array_equal(port.img_logpolar_blur(la), ref.img_logpolar_blur(lb))
             assert np.array_equal(port.img_interpolate_logpolar(la, W, H, cx, cy),
                                   ref.img_interpolate_logpolar(lb, W, H, cx, cy))
+
+
+@pytest.mark.skipif(not O.ref_available(), reason="reference library not built / not present")
+@pytest.mark.parametrize("W,H", [(1920, 1080), (3840, 1920)])
+def test_port_matches_reference_library_full_sizes(W, H):
+    """The restatement against the reference's own kernels at the benchmark geometries (not only the
+    400x232 case above): SAT, reduced buffer and un-warped frame over every test gaze, and the
+    log-polar path at the first three."""
+    port, ref = O.Oracle("port"), O.Oracle("ref")
+    ncpu = len(os.sched_getaffinity(0))
+    port.set_threads(ncpu)
+    ref.set_threads(ncpu)
+    ow, oh = O.reduced_size(W), O.reduced_size(H)
+    frame = O.lcg_frame(W, H, 77)
+    sp, sr = port.sat_encode(frame), ref.sat_encode(frame)
+    assert np.array_equal(sp, sr)
+    del sr
+    grid = port.sat_create_grid(ow, oh, W, H)
+    assert np.array_equal(grid, ref.sat_create_grid(ow, oh, W, H))
+    for k, (cx, cy) in enumerate(GAZES):
+        a = port.sat_sample_rect(sp, ow, oh, cx, cy, grid=grid)
+        assert np.array_equal(a, ref.sat_sample_rect(sp, ow, oh, cx, cy, grid=grid)), (cx, cy)
+        assert np.array_equal(port.sat_interpolate_rect(a, W, H, cx, cy),
+                              ref.sat_interpolate_rect(a, W, H, cx, cy)), (cx, cy)
+        if k < 3:
+            la = port.img_sample_logpolar(frame, ow, oh, cx, cy)
+            assert np.array_equal(la, ref.img_sample_logpolar(frame, ow, oh, cx, cy))
+            assert np.array_equal(port.img_logpolar_blur(la), ref.img_logpolar_blur(la))
+            assert np.array_equal(port.img_interpolate_logpolar(la, W, H, cx, cy),
+                                  ref.img_interpolate_logpolar(la, W, H, cx, cy))
 
 
 def test_gnomonic_golden_vectors(oracle):
