@@ -281,6 +281,24 @@ def cpu_baseline(W, H, ow, oh, budget_s=12.0, max_frames=64, centre_only=False):
                       "(3 ctypes calls per frame)" % (n, W, H, ow, oh, dt)}
 
 
+def cpu_encode_frame_cpu(W, H, budget_s=2.0, max_frames=16):
+    """SURVEY 8(d) CPU baseline (2): SATEncoder::EncodeFrameCPU (sat_encoder.cc:137-185) compiled
+    from the reference's own text - the SAT stage only, scalar and single-threaded as shipped."""
+    orc, kind = load_cpu_oracle()
+    if kind != "reference" or not hasattr(orc, "_sat_encode_cpu"):
+        return None
+    frame = np.ascontiguousarray(synth_frame(W, H, 1))
+    sat = np.zeros((H, W, 3), np.uint32)
+    orc.sat_encode_cpu(frame, out=sat)
+    n, t0 = 0, time.perf_counter()
+    while n < max_frames and (n == 0 or time.perf_counter() - t0 < budget_s):
+        orc.sat_encode_cpu(frame, out=sat)
+        n += 1
+    dt = time.perf_counter() - t0
+    return {"value": n / dt, "unit": "frames/s (SAT build only)", "cores": 1, "kind": "reference",
+            "sample": "%d SAT build(s) of %dx%d by SATEncoder::EncodeFrameCPU in %.1f s" % (n, W, H, dt)}
+
+
 def run_reference_arm(args, W, H, ow, oh, rank):
     if rank != 0:
         return
@@ -881,6 +899,9 @@ def run_configs(args, fov, m, device, rank, world, dist, peak):
         if not args.no_cpu_baseline:
             c0["cpu_reference"] = cpu_baseline(W1, H1, reduced(W1), reduced(H1), budget_s=3.0,
                                                max_frames=32, centre_only=True)
+            twin = cpu_encode_frame_cpu(W1, H1)
+            if twin:
+                c0["cpu_reference_encode_frame_cpu"] = twin
         out["1080p_centre_gaze"] = c0
     return out
 

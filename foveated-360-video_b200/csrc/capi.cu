@@ -34,6 +34,11 @@ struct fov_ctx {
 
 namespace fov {
 
+bool pdl_enabled() {
+  static const bool on = getenv("FOV360_NO_PDL") == nullptr;
+  return on;
+}
+
 cudaEvent_t Profiler::get() {
   if (!pool.empty()) {
     cudaEvent_t e = pool.back();

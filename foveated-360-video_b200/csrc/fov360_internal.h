@@ -6,6 +6,7 @@
 #include <map>
 #include <string>
 #include <tuple>
+#include <utility>
 #include <vector>
 
 #include "fov360.h"
@@ -138,6 +139,36 @@ class KernelScope {
   Profiler::Pending p_{};
   bool on_ = false;
 };
+
+// ---- programmatic dependent launch (the encode -> sample -> interpolate chain) ----------------
+// A kernel launched with launch_chained() may become resident while its predecessor in the stream
+// is still draining: CTA scheduling and whatever it does before pdl_wait() (table look-ups, shared
+// memory set-up - nothing a predecessor could have produced) overlap the predecessor's tail.
+// Every chained kernel executes pdl_wait() before it touches frame data, so the ordering the
+// in-order queue promises (sat_encoder.cc:67-135 ... sat_decoder.cc:887-927 rely on it) still holds
+// transitively; pdl_trigger() at its start lets its own successor do the same.
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+bool pdl_enabled();  // capi.cu: on unless FOV360_NO_PDL is set
+
+template <class... KArgs, class... Args>
+cudaError_t launch_chained(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                           cudaStream_t stream, Args &&...args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(std::forward<Args>(args))...);
+}
+#endif
 
 // ---- kernel launchers (one per .cu) ----------------------------------------------------------
 

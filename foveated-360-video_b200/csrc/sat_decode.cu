@@ -105,6 +105,7 @@ __global__ void __launch_bounds__(32 * kSampleWarps, FOV360_SAMPLE_MIN_CTAS)
     sat_sample_rect_kernel(const SampleArgs a,
                                                                             const GazeBatch g) {
   __shared__ SampleRow srow[kSampleWarps * kSampleRows];
+  pdl_trigger();
   const int lane = threadIdx.x, warp = threadIdx.y;
   const int i = blockIdx.x * kSampleCols + lane;
   const int jb = blockIdx.y * kSampleWarps * kSampleRows;
@@ -166,6 +167,7 @@ __global__ void __launch_bounds__(32 * kSampleWarps, FOV360_SAMPLE_MIN_CTAS)
   uint32_t *orow = reinterpret_cast<uint32_t *>(a.out + (size_t)f * a.out_stride) +
                    (size_t)j0 * a.o_linesize_px + i;
 
+  pdl_wait();  // everything above came from the edge tables; the SAT and the frames follow
   if (a.src != nullptr) {
     // 1:1 warps: every live box is one pixel wide and every sampled row one pixel high.
     bool unit = !live || dx == 1u;
@@ -394,6 +396,7 @@ __global__ void __launch_bounds__(32 * kInterpWarps, FOV360_INTERP_MIN_CTAS)
   __shared__ float4 vstage[kInterpWarps][kStage];
   __shared__ RowSel rowsel[kInterpWarps][kInterpRows];
   __shared__ int4 xsel[kInterpPx][32];
+  pdl_trigger();
   const int lane = threadIdx.x, warp = threadIdx.y;
   const int x4 = (blockIdx.x * 32 + lane) * kInterpPx;
   const int y0 = (blockIdx.y * kInterpWarps + warp) * kInterpRows;
@@ -492,6 +495,7 @@ __global__ void __launch_bounds__(32 * kInterpWarps, FOV360_INTERP_MIN_CTAS)
 #ifdef FOV360_INTERP_FORCE_GENERIC
   simple = false;
 #endif
+  pdl_wait();  // both axes are resolved from the tables; the reduced buffer is read from here on
 
   auto store_row = [&](const uint32_t (&px)[kInterpPx]) {
     if (vec_ok) {
@@ -913,8 +917,7 @@ cudaError_t launch_sat_sample_rect(const LaunchCtx &lc, int n, uint8_t *out, siz
                   (oh + kSampleWarps * kRows - 1) / (kSampleWarps * kRows), n),
       block(32, kSampleWarps);
   KernelScope ks(lc, "sat_sample_rect");
-  sat_sample_rect_kernel<kRows><<<grid, block, 0, lc.stream>>>(a, gaze);
-  return cudaGetLastError();
+  return launch_chained(sat_sample_rect_kernel<kRows>, grid, block, 0, lc.stream, a, gaze);
 }
 
 cudaError_t launch_sat_interpolate_rect(const LaunchCtx &lc, int n, uint8_t *out, size_t out_stride,
@@ -946,13 +949,9 @@ cudaError_t launch_sat_interpolate_rect(const LaunchCtx &lc, int n, uint8_t *out
                   (H + kInterpWarps * rows - 1) / (kInterpWarps * rows), n),
       block(32, kInterpWarps);
   KernelScope ks(lc, "sat_interpolate_rect");
-  if (rows == 8)
-    sat_interpolate_rect_kernel<8><<<grid, block, 0, lc.stream>>>(a, gaze);
-  else if (rows == 16)
-    sat_interpolate_rect_kernel<16><<<grid, block, 0, lc.stream>>>(a, gaze);
-  else
-    sat_interpolate_rect_kernel<32><<<grid, block, 0, lc.stream>>>(a, gaze);
-  return cudaGetLastError();
+  if (rows == 8) return launch_chained(sat_interpolate_rect_kernel<8>, grid, block, 0, lc.stream, a, gaze);
+  if (rows == 16) return launch_chained(sat_interpolate_rect_kernel<16>, grid, block, 0, lc.stream, a, gaze);
+  return launch_chained(sat_interpolate_rect_kernel<32>, grid, block, 0, lc.stream, a, gaze);
 }
 
 cudaError_t launch_sat_interpolate_gnomonic(const LaunchCtx &lc, uint8_t *out, int tw, int th,

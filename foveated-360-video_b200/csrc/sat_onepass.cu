@@ -125,8 +125,10 @@ __global__ void __launch_bounds__(kMaxWarps * 32, MIN_CTAS) sat_onepass_kernel(c
   const int RS = a.R;                  // row stride of the per-warp row-sum table
   uint4 *s_left = s_rs + NW * RS;      // [R] carry from the CTAs to the left
 
-  if (threadIdx.x == 0) s_ticket = atomicAdd(&a.counters[0], 1u);
+  pdl_trigger();
   if ((int)threadIdx.x < RS) s_left[threadIdx.x] = make_uint4(0, 0, 0, 0);
+  pdl_wait();  // the frames (and the scratch of an earlier SAT build) are final from here on
+  if (threadIdx.x == 0) s_ticket = atomicAdd(&a.counters[0], 1u);
   __syncthreads();
   const uint32_t tile = s_ticket;  // (band, frame, strip) order
   FOV_TRACE(0);
@@ -491,8 +493,7 @@ cudaError_t launch_sat_onepass(const LaunchCtx &lc, int n, uint32_t *sat, size_t
     cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
   });
   KernelScope ks(lc, "sat_onepass");
-  kernel<<<a.total_tiles, p.NW * 32, smem, lc.stream>>>(a);
-  return cudaGetLastError();
+  return launch_chained(kernel, dim3(a.total_tiles), dim3(p.NW * 32), smem, lc.stream, a);
 }
 
 }  // namespace fov

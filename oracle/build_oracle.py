@@ -68,7 +68,7 @@ def build_ref(force: bool = False) -> str | None:
     entry = os.path.join(shim, "ref_entry.cc")
     if not os.path.isdir(REF_DIR):
         return out if os.path.exists(out) else None
-    srcs = [os.path.join(REF_DIR, f) for f in CL_FILES]
+    srcs = [os.path.join(REF_DIR, f) for f in CL_FILES] + [os.path.join(REF_DIR, "sat_encoder.cc")]
     if not force and _newer(out, srcs + [entry, os.path.join(shim, "clshim.h"), __file__]):
         return out
     os.makedirs(out_dir, exist_ok=True)
@@ -79,6 +79,13 @@ def build_ref(force: bool = False) -> str | None:
                 text = fh.read()
             with open(os.path.join(tmp, f + ".inc"), "w") as fh:
                 fh.write(VEC_LITERAL.sub(r"\1(", text))
+        # SATEncoder::EncodeFrameCPU: the function's text, signature line to closing brace
+        with open(os.path.join(REF_DIR, "sat_encoder.cc")) as fh:
+            cc = fh.read().split("\n")
+        a = next(i for i, ln in enumerate(cc) if ln.startswith("void SATEncoder::EncodeFrameCPU("))
+        z = next(i for i in range(a + 1, len(cc)) if cc[i].startswith("}"))
+        with open(os.path.join(tmp, "encode_frame_cpu.cc.inc"), "w") as fh:
+            fh.write("\n".join(cc[a:z + 1]) + "\n")
         cmd = ["g++", "-std=c++17", *COMMON, "-w", "-I", shim, "-I", tmp, "-o", out, entry]
         subprocess.check_call(cmd)
     finally:

@@ -42,6 +42,24 @@ namespace ref_proj {  // last: its #define PI / PI_2 / DEG2RAD / RAD2DEG are not
 #include "projections_program.cl.inc"
 }
 
+// SATEncoder::EncodeFrameCPU (sat_encoder.cc:137-185), the reference's host-side SAT build: the
+// function's own text, extracted by build_oracle.py, compiled against the two struct members it
+// reads.  Scalar, single-threaded, column-major loops - exactly as the reference ships it.
+namespace ref_cpu {
+struct AVCodecContext {
+  int width, height;
+};
+struct AVFrame {
+  uint8_t *data[8];
+  int linesize[8];
+};
+class SATEncoder {
+ public:
+  void EncodeFrameCPU(uint32_t *target_frame, AVCodecContext *codec_ctx, AVFrame *frame);
+};
+#include "encode_frame_cpu.cc.inc"
+}  // namespace ref_cpu
+
 namespace {
 
 int g_threads = 0;  // 0 = OpenMP default
@@ -95,6 +113,15 @@ extern "C" {
 
 void ref_set_threads(int n) { g_threads = n; }
 int ref_get_threads(void) { return g_threads > 0 ? g_threads : omp_get_max_threads(); }
+
+// SATEncoder::EncodeFrameCPU, sat_encoder.cc:137-185.
+void ref_sat_encode_cpu(uint32_t *sat, const uint8_t *src, int W, int H, int src_linesize) {
+  ref_cpu::AVCodecContext ctx{W, H};
+  ref_cpu::AVFrame frame = {};
+  frame.data[0] = const_cast<uint8_t *>(src);
+  frame.linesize[0] = src_linesize;
+  ref_cpu::SATEncoder().EncodeFrameCPU(sat, &ctx, &frame);
+}
 
 // SATEncoder::EncodeFrameGPU, sat_encoder.cc:67-135 (three in-order launches).
 void ref_sat_encode(uint32_t *sat, const uint8_t *src, int W, int H, int src_linesize) {

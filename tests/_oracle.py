@@ -67,6 +67,8 @@ class Oracle:
         self._set_threads = sig("set_threads", _i)
         self._get_threads = sig("get_threads", res=_i)
         self._sat_encode = sig("sat_encode", _u32p, _u8p, _i, _i, _i)
+        if kind == "ref" and hasattr(L, "ref_sat_encode_cpu"):
+            self._sat_encode_cpu = sig("sat_encode_cpu", _u32p, _u8p, _i, _i, _i)
         self._sat_create_grid = sig("sat_create_grid", _i16p, _i, _i, _i, _i)
         self._sat_sample_rect = sig("sat_sample_rect", _u8p, _i, _i, _i, _u32p, _i, _i, _i16p, _f, _f)
         self._sat_interpolate_rect = sig("sat_interpolate_rect", _u8p, _i, _i, _u8p, _i, _i, _f, _f)
@@ -106,6 +108,13 @@ class Oracle:
         H, W, bpp = frame.shape
         sat = np.empty((H, W, 3), np.uint32)
         self._sat_encode(sat, np.ascontiguousarray(frame), W, H, W * bpp)
+        return sat
+
+    def sat_encode_cpu(self, frame: np.ndarray, out=None) -> np.ndarray:
+        """SATEncoder::EncodeFrameCPU (sat_encoder.cc:137-185): the reference's host twin ("ref" only)."""
+        H, W, bpp = frame.shape
+        sat = np.empty((H, W, 3), np.uint32) if out is None else out
+        self._sat_encode_cpu(sat, np.ascontiguousarray(frame), W, H, W * bpp)
         return sat
 
     def sat_create_grid(self, ow: int, oh: int, W: int, H: int) -> np.ndarray:

@@ -134,6 +134,18 @@ def test_port_matches_reference_library_full_sizes(W, H):
                                   ref.img_interpolate_logpolar(la, W, H, cx, cy))
 
 
+@pytest.mark.skipif(not O.ref_available(), reason="reference library not built / not present")
+def test_encode_frame_cpu_twin_agrees():
+    """SURVEY 8(a13): SATEncoder::EncodeFrameCPU (the reference's host code, compiled from its own
+    text) builds the same table as its OpenCL kernels and as the restatement - wrap-around included."""
+    port, ref = O.Oracle("port"), O.Oracle("ref")
+    for frame in (O.lcg_frame(400, 232, 5), O.lcg_frame(250, 130, 6)[..., :3].copy(),
+                  np.full((512, 640, 4), 255, np.uint8)):
+        want = ref.sat_encode_cpu(frame)
+        assert np.array_equal(want, ref.sat_encode(frame))
+        assert np.array_equal(want, port.sat_encode(frame))
+
+
 def test_gnomonic_golden_vectors(oracle):
     """Projections::GnomonicProjection restatement against viewports rendered by the reference's
     own kernel (tests/golden/make_golden.py: complete arrays of a small frame, hashes at 1080p)."""

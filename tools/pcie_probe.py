@@ -1,9 +1,28 @@
 #!/usr/bin/env python3
 """PCIe ceiling of the box: pinned H2D alone, D2H alone, both at once (torch, two streams).
-The e2e leg of bench.py moves 118 MB each way per 8K frame; this is the number it is bound by."""
+The e2e leg of bench.py moves 118 MB each way per 8K frame; this is the number it is bound by.
+
+Single process: one GPU.  Under torchrun (`python -m torch.distributed.run --nproc-per-node N
+--master-addr 127.0.0.1 tools/pcie_probe.py`) every rank drives its own GPU at the SAME time (a
+barrier separates the phases), so the output is the concurrent ceiling of the N links - what the
+e2e legs of an N-GPU bench.py run share."""
+import json
+import os
+import time
+
 import torch
 
-n = 1 << 30
+rank = int(os.environ.get("RANK", 0))
+world = int(os.environ.get("WORLD_SIZE", 1))
+local = int(os.environ.get("LOCAL_RANK", 0))
+torch.cuda.set_device(local)
+dist = None
+if world > 1:
+    import torch.distributed as dist
+
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+n = 1 << 29
 h_in = torch.empty(n, dtype=torch.uint8).pin_memory()
 h_out = torch.empty(n, dtype=torch.uint8).pin_memory()
 d_a = torch.empty(n, dtype=torch.uint8, device="cuda")
@@ -11,16 +30,17 @@ d_b = torch.empty(n, dtype=torch.uint8, device="cuda")
 s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
 
 
-def timed(fn, reps=5):
+def timed(fn, reps=8):
     fn()
     torch.cuda.synchronize()
-    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    a.record()
+    if dist:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
     for _ in range(reps):
         fn()
-    b.record()
     torch.cuda.synchronize()
-    return a.elapsed_time(b) / reps
+    return (time.perf_counter() - t0) / reps
 
 
 def h2d():
@@ -32,20 +52,26 @@ def d2h():
 
 
 def both():
-    ev = torch.cuda.Event()
-    ev.record()
-    s1.wait_event(ev)
-    s2.wait_event(ev)
     with torch.cuda.stream(s1):
         d_a.copy_(h_in, non_blocking=True)
     with torch.cuda.stream(s2):
         h_out.copy_(d_b, non_blocking=True)
-    torch.cuda.current_stream().wait_stream(s1)
-    torch.cuda.current_stream().wait_stream(s2)
 
 
 gb = n / 1e9
-print("H2D alone  %.1f GB/s" % (gb / timed(h2d) * 1e3))
-print("D2H alone  %.1f GB/s" % (gb / timed(d2h) * 1e3))
-t = timed(both)
-print("both       %.1f GB/s each way (%.1f fps of 8K frames)" % (gb / t * 1e3, gb / t * 1e3 / 0.11796))
+res = {"h2d_alone": gb / timed(h2d), "d2h_alone": gb / timed(d2h), "both_each_way": gb / timed(both)}
+if dist:
+    t = torch.tensor([res["h2d_alone"], res["d2h_alone"], res["both_each_way"]], device="cuda",
+                     dtype=torch.float64)
+    allr = [torch.zeros_like(t) for _ in range(world)]
+    dist.all_gather(allr, t)
+    if rank == 0:
+        rows = [[round(float(v), 1) for v in r.tolist()] for r in allr]
+        tot = [round(sum(r[k] for r in rows), 1) for k in range(3)]
+        print(json.dumps({"gpus_concurrent": world, "unit": "GB/s",
+                          "per_rank[h2d_alone,d2h_alone,both_each_way]": rows, "total": tot,
+                          "8k_frames_per_s_at_both_total": round(tot[2] / 0.11796, 1)}))
+    dist.destroy_process_group()
+else:
+    print(json.dumps({"gpus_concurrent": 1, "unit": "GB/s", **{k: round(v, 1) for k, v in res.items()},
+                      "8k_frames_per_s_at_both": round(res["both_each_way"] / 0.11796, 1)}))
