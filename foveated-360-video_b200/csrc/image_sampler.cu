@@ -221,7 +221,10 @@ __device__ __forceinline__ bool logpolar_hits(const LpInterpArgs &a, int i, int 
   return calc_x == x && calc_y == y;                                          // :53
 }
 
-__global__ void __launch_bounds__(kLpThreads, 4) img_interpolate_logpolar_kernel(const LpInterpArgs a) {
+#ifndef FOV360_LP_MIN_CTAS
+#define FOV360_LP_MIN_CTAS 4
+#endif
+__global__ void __launch_bounds__(kLpThreads, FOV360_LP_MIN_CTAS) img_interpolate_logpolar_kernel(const LpInterpArgs a) {
   __shared__ LpRow srows[kLpMaxRows];
   const int W = a.W, H = a.H, ow = a.ow, oh = a.oh;
   const int xx = blockIdx.x * kLpThreads + threadIdx.x;

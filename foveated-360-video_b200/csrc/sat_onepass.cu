@@ -63,13 +63,21 @@ struct OnePassArgs {
   uint4 *rowagg;       // [tile][kMaxBandRows]  {r, g, b, epoch << 2 | kRow}: per-row sums of a CTA tile
   uint4 *colagg;       // [tile][NW][4][32]     {v0, v1, v2, epoch << 2 | state}: column carry
 #ifdef FOV360_SAT_TRACE
-  long long *trace;  // [tile][8] clock64 at the phase boundaries (tools/sat_trace.cu only)
+  long long *trace;  // [tile][16] clock64, then %globaltimer, at the 8 phase boundaries (tools/sat_trace.cu only)
 #endif
 };
 
 #ifdef FOV360_SAT_TRACE
-#define FOV_TRACE(i) \
-  if (threadIdx.x == 0) a.trace[(size_t)tile * 8 + (i)] = clock64()
+__device__ __forceinline__ long long trace_globaltimer() {
+  long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define FOV_TRACE(i)                                                  \
+  if (threadIdx.x == 0) {                                             \
+    a.trace[(size_t)tile * 16 + (i)] = clock64();                     \
+    a.trace[(size_t)tile * 16 + 8 + (i)] = trace_globaltimer();       \
+  }
 #else
 #define FOV_TRACE(i)
 #endif
