@@ -1,7 +1,9 @@
 #!/usr/bin/env python3
 """BASELINE configs[4]: concurrent 4K streams with independent per-frame gaze
 traces, stream s pinned to GPU s % G, the streams of one GPU foveated by one batched call per frame
-time.  Run under torchrun for G > 1; a single process plays rank 0 of `--world` GPUs.
+time, host wall clock with the stream synchronised after every frame time (the same measurement
+`bench.py` reports as `configs.serving_4k_streams`; this tool adds gaze-trace files and the encoder
+surface).  Run under torchrun for G > 1; a single process plays rank 0 of `--world` GPUs.
 
     python tools/serve_bench.py [--streams 64] [--world 8] [--frames 300]
     python -m torch.distributed.run --nproc-per-node 8 tools/serve_bench.py
@@ -19,17 +21,7 @@ sys.path.insert(0, ROOT)
 import bench  # noqa: E402
 
 
-def gaze_walk(stream: int, frames: int) -> np.ndarray:
-    """Smooth random walk, sigma 0.01 per frame, reflected at 0 and 1, seeded by the stream id."""
-    rng = np.random.default_rng(stream)
-    p = rng.random(2)
-    out = np.empty((frames, 2), np.float32)
-    for t in range(frames):
-        p = p + rng.normal(0.0, 0.01, 2)
-        p = np.abs(p)
-        p = 1.0 - np.abs(1.0 - p)
-        out[t] = p
-    return out
+gaze_walk = bench.gaze_walk
 
 
 ap = argparse.ArgumentParser()
@@ -80,15 +72,20 @@ def frame_time(t):
         conv.RGB0ToNV12Frames(n, ny, ow * oh, ow, nuv, ow * oh // 2, ow, red, rb, 4 * ow, ow, oh)
 
 
+import time  # noqa: E402
+
 for t in range(3):
     frame_time(t)
-m.profile_reset()
-m.profile(True)
+m.Finish()
+if dist:
+    dist.barrier()
+# Host wall clock; the stream is synchronised after every frame time (a server delivers each frame
+# before it takes the next one), so launch gaps and the wait itself are inside the number.
+t0 = time.perf_counter()
 for t in range(args.frames):
     frame_time(3 + t)
-tot = m.profile_totals()
-m.profile(False)
-sec = sum(v[0] for v in tot.values()) / 1e3
+    m.Finish()
+sec = time.perf_counter() - t0
 sec = fov.sharding.reduce_max_seconds(sec, dist, "cuda" if dist else None)
 if rank == 0:
     ranks = int(os.environ.get("WORLD_SIZE", 1)) if dist else 1
