@@ -41,7 +41,10 @@ struct GatherArgs {
   float cx, cy;
 };
 
-constexpr int kGatherRows = 4;  // reduced rows per thread: that many independent gathers in flight
+#ifndef FOV360_GATHER_ROWS
+#define FOV360_GATHER_ROWS 4
+#endif
+constexpr int kGatherRows = FOV360_GATHER_ROWS;  // reduced rows per thread: that many independent gathers in flight
 
 __global__ void __launch_bounds__(256) img_sample_rect_kernel(const GatherArgs a,
                                                               const int16_t *__restrict__ xd,
@@ -419,7 +422,10 @@ __global__ void __launch_bounds__(256) img_logpolar_blur_kernel(uint32_t *__rest
 // vertically first (top + bottom of a column is shared by three output pixels); only the three
 // weighted products and their two sums (:123-136) are float operations, rounded one by one like the
 // reference's.
-constexpr int kBlurRows = 8;   // rows per warp
+#ifndef FOV360_BLUR_ROWS
+#define FOV360_BLUR_ROWS 8
+#endif
+constexpr int kBlurRows = FOV360_BLUR_ROWS;   // rows per warp
 constexpr int kBlurChunk = 4;  // rows requested together
 constexpr int kBlurWarps = 4;
 

@@ -51,3 +51,23 @@ def test_product_arm_line():
     cb = d["cpu_baseline"]
     assert cb["kind"] in ("reference", "port") and cb["value"] > 0 and cb["cores"] >= 1
     assert d["value"] / cb["value"] > 10
+    # round 2: the traffic entry says where it comes from and whether the kernel changed since
+    assert {"traffic", "traffic_source", "traffic_state"} <= set(r)
+    assert all("frac" in k and "alg_gbs" in k for k in r["kernels"].values())
+    # the server-shaped lane moves NV12 up and the reduced NV12 buffer down
+    es = d["e2e_server"]
+    assert es["h2d_bytes_per_step"] == 4 * 1920 * 1080 * 3 // 2
+    assert es["d2h_bytes_per_step"] == 4 * 1072 * 608 * 3 // 2 and es["value"] > d["e2e"]["value"]
+    # every other BASELINE configuration is in the same line
+    cfg = d["configs"]
+    assert {"4k_gaze_sweep_single", "4k_gaze_sweep_batch8", "8k_single_frame",
+            "4k_logpolar_vs_logrect", "serving_4k_streams", "1080p_centre_gaze"} <= set(cfg)
+    for name in ("4k_gaze_sweep_single", "4k_gaze_sweep_batch8", "8k_single_frame"):
+        assert cfg[name]["frames_per_s"] > 0 and 0 < cfg[name]["pipeline_frac"] < 1.2
+        assert set(cfg[name]["kernels"]) == {"sat_onepass", "sat_sample_rect", "sat_interpolate_rect"}
+    lp = cfg["4k_logpolar_vs_logrect"]
+    assert set(lp["kernels"]) == {"img_sample_logpolar", "img_logpolar_blur", "img_interpolate_logpolar"}
+    sv = cfg["serving_4k_streams"]
+    assert sv["streams_per_gpu"] == 8 and sv["resident"]["frames_per_s"] > 0
+    assert "perf_counter" in sv["resident"]["timing"] and sv["server_lane"]["value"] > 0
+    assert cfg["1080p_centre_gaze"]["cpu_reference"]["value"] > 0
