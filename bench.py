@@ -724,8 +724,10 @@ def run_logrect_small(fov, m, stream, W, H, B, gazes, reps, peak):
     m.Finish()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
+    t_host = time.perf_counter()
     for i in range(nsteps * reps):
         step(i)
+    t_host = time.perf_counter() - t_host  # the host only enqueues: nothing waits inside the loop
     e1.record(stream)
     m.Finish()
     ms = e0.elapsed_time(e1)
@@ -744,6 +746,7 @@ def run_logrect_small(fov, m, stream, W, H, B, gazes, reps, peak):
     fps = B * nsteps * reps / (ms * 1e-3)
     return {"frames_per_call": B, "gaze_points": int(len(gazes)), "calls_timed": nsteps * reps,
             "frames_per_s": round(fps, 1), "ms_per_call": round(ms / (nsteps * reps), 4),
+            "host_enqueue_ms_per_call": round(1e3 * t_host / (nsteps * reps), 4),
             "pipeline_frac": round(ab["total"] * fps / 1e9 / peak, 4),
             "l2": "ring of %d buffer sets (%.0f MB each): no step finds its inputs in L2" % (
                 ring, B * (2 * fb + sb + rb) / 1e6),

@@ -423,7 +423,7 @@ __global__ void __launch_bounds__(256) img_logpolar_blur_kernel(uint32_t *__rest
 // weighted products and their two sums (:123-136) are float operations, rounded one by one like the
 // reference's.
 #ifndef FOV360_BLUR_ROWS
-#define FOV360_BLUR_ROWS 8
+#define FOV360_BLUR_ROWS 4
 #endif
 constexpr int kBlurRows = FOV360_BLUR_ROWS;   // rows per warp
 constexpr int kBlurChunk = 4;  // rows requested together
