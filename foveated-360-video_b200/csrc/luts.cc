@@ -151,13 +151,15 @@ void build_logpolar_lntab(int ow, std::vector<double2> &tab) {
 }
 
 // Half-width of the band around n + 0.5 inside which the single-precision j_f of the inverse
-// log-polar warp may round to the other index than the reference's: both values are within
-// 3e-7 rad of the true angle (float division, atanf, polynomial) times oh / 2 pi, and each is
-// rounded once to the float spacing at "j_f + 2 oh" <= 2.75 oh.
+// log-polar warp may round to the other index than the reference's.  Both values are within 3e-7 rad
+// of the true angle (reference: float division + atanf, 1.5e-7; device: reciprocal, polynomial and
+// its evaluation, 2.6e-7) times oh / 2 pi; the reference then rounds the scaled angle to float
+// (<= a quarter of the spacing at "j_f + 2 oh" <= 2.75 oh, being at least one binade smaller) and
+// the "+ 2 oh" sum (half a spacing), the device rounds once (half a spacing): 1.25 spacings, 1.5 here.
 float logpolar_round_zone(int oh) {
   const float top = 2.75f * oh;
   const float quantum = nextafterf(top, INFINITY) - top;
-  return (float)(6e-7 * oh / (2.0 * 3.14159265358979323846)) + quantum;
+  return (float)(6e-7 * oh / (2.0 * 3.14159265358979323846)) + 1.5f * quantum;
 }
 
 // Gnomonic viewport constants (projections_program.cl:25-28): (center - 0.5) is promoted to

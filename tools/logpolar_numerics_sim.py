@@ -86,7 +86,7 @@ def fast_j(dx, dy, oh):
 W, H = int(sys.argv[1]), int(sys.argv[2])
 ow, oh = 16 * math.ceil(W / 1.8 / 16), 16 * math.ceil(H / 1.8 / 16)
 top = f32(2.75 * oh)
-zone = f32(6e-7 * oh / (2 * math.pi)) + (np.nextafter(top, f32(np.inf)) - top)
+zone = f32(6e-7 * oh / (2 * math.pi)) + f32(1.5) * (np.nextafter(top, f32(np.inf)) - top)
 tab = lntab(ow)
 print("%dx%d -> %dx%d, zone %.3e" % (W, H, ow, oh, zone))
 for cx, cy in [(0.5, 0.5), (0.65, 0.75), (0.02, 0.3), (1.0, 1.0)]:
