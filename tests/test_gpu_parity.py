@@ -580,6 +580,44 @@ def test_encode_sample_batched_equals_separate_calls(dev, fov, oracle):
         assert np.array_equal(got_red[f], want), f
 
 
+def test_launch_chain_keeps_queue_order(dev, fov, oracle):
+    """The encode / sample / interpolate kernels are launched with programmatic dependent launch
+    (their CTAs may become resident while the predecessor drains).  The in-order semantics of the
+    queue must survive: here every call consumes what the previous one produced, in the SAME
+    buffers and with no host synchronisation in between - the un-warped frame of pass k is the
+    source of pass k + 1 (what run_satlogrectilinear.cc:926-943 does with cl_source_frame) - and
+    the final buffers must equal the same chain evaluated by the oracle."""
+    W, H = 640, 360
+    ow, oh = fov.reduced_dim(W), fov.reduced_dim(H)
+    frame = O.smooth_frame(W, H, seed=11)
+    gazes = [(0.5, 0.5), (0.31, 0.77), (0.98, 0.05), (0.02, 0.6), (0.66, 0.33), (1.0, 1.0)]
+    img = dev.m.upload(frame)
+    sat, red = dev.m.Buffer(12 * W * H), dev.m.upload(np.zeros((oh, ow, 4), np.uint8))
+    for cx, cy in gazes:  # nothing waits inside this loop
+        dev.enc.EncodeFrameGPU(sat, img, W, H, 4 * W)
+        dev.dec.SampleFrameRectGPU(red, ow, oh, 4 * ow, sat, W, H, cx, cy)
+        dev.dec.InterpolateFrameRectGPU(img, W, H, 4 * W, red, ow, oh, 4 * ow, cx, cy)
+    got_img = dev.m.copy_to_host(np.empty((H, W, 4), np.uint8), img)
+    got_red = dev.m.copy_to_host(np.empty((oh, ow, 4), np.uint8), red)
+    want_img, want_red = frame, np.zeros((oh, ow, 4), np.uint8)
+    for cx, cy in gazes:
+        want_sat = oracle.sat_encode(want_img)
+        want_red = oracle.sat_sample_rect(want_sat, ow, oh, cx, cy, out=want_red)
+        want_img = oracle.sat_interpolate_rect(want_red, W, H, cx, cy)
+    assert np.array_equal(got_red, want_red)
+    assert np.array_equal(got_img, want_img)
+    # the batched, fused form through the same buffers, twice in a row with different gazes
+    fov.FoveateFramesGPU(dev.m, 1, img, 4 * W * H, red, 4 * ow * oh, sat, 12 * W * H, img, 4 * W * H,
+                         W, H, 4 * W, ow, oh, np.asarray([gazes[1]], np.float32))
+    fov.FoveateFramesGPU(dev.m, 1, img, 4 * W * H, red, 4 * ow * oh, sat, 12 * W * H, img, 4 * W * H,
+                         W, H, 4 * W, ow, oh, np.asarray([gazes[2]], np.float32))
+    for cx, cy in (gazes[1], gazes[2]):
+        want_sat = oracle.sat_encode(want_img)
+        want_red = oracle.sat_sample_rect(want_sat, ow, oh, cx, cy, out=want_red)
+        want_img = oracle.sat_interpolate_rect(want_red, W, H, cx, cy)
+    assert np.array_equal(dev.m.copy_to_host(np.empty((H, W, 4), np.uint8), img), want_img)
+
+
 # --------------------------------------------------------- directly against the reference ----
 @pytest.mark.skipif(not O.ref_available(), reason="oracle/_ref/libfovref.so not present")
 def test_8k_frame_against_reference_library(dev):
