@@ -11,6 +11,7 @@ from ._capi import PROTOTYPES, header_symbols, library_path, load  # noqa: F401
 from .host import (  # noqa: F401
     DeviceBuffer,
     EncodeSampleFramesGPU,
+    FoveateFramesDeviceGazeGPU,
     FoveateFramesGPU,
     FovError,
     GazeViewPoints,

@@ -52,6 +52,14 @@ PROTOTYPES = {
                                      _i, _i, _i, _i, _i, _fp]),
     "fov_sat_encode_sample_batched": (_i, [_vp, _i, _vp, _sz, _vp, _sz, _vp, _sz,
                                            _i, _i, _i, _i, _i, _fp]),
+    "fov_sat_encode_sample_batched_dev": (_i, [_vp, _i, _vp, _sz, _vp, _sz, _vp, _sz,
+                                               _i, _i, _i, _i, _i, _vp]),
+    "fov_sat_foveate_batched_dev": (_i, [_vp, _i, _vp, _sz, _vp, _sz, _vp, _sz, _vp, _sz,
+                                         _i, _i, _i, _i, _i, _vp]),
+    "fov_graph_begin_capture": (_i, [_vp]),
+    "fov_graph_end_capture": (_i, [_vp, C.POINTER(_vp)]),
+    "fov_graph_launch": (_i, [_vp, _vp]),
+    "fov_graph_destroy": (None, [_vp, _vp]),
     "fov_img_grid_init": (_i, [_vp, _i, _i, _i, _i]),
     "fov_img_grid_export": (_i, [_vp, _vp, _i, _i, _i, _i]),
     "fov_img_sample_rect": (_i, [_vp, _vp, _i, _i, _i, _vp, _i, _i, _i, _f, _f]),

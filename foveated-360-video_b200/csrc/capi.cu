@@ -18,10 +18,12 @@ struct fov_ctx {
   std::string last_error;
   uint64_t launches = 0;
   Profiler prof;
-  LaunchCtx lc() { return LaunchCtx{stream, sm_count, device, &prof, &launches}; }
+  // per-kernel event timing is off while a graph is being captured (the events would be replayed)
+  LaunchCtx lc() { return LaunchCtx{stream, sm_count, device, capturing ? nullptr : &prof, &launches}; }
   SatScratch sat_scratch;
   bool sat_scratch_dirty = true;  // holds bytes that are not carry units of an earlier epoch
-  uint32_t sat_epoch = 0;         // grows monotonically: one value per one-pass launch
+  uint32_t sat_epoch = 0;         // one-pass launches since the last clear (the epoch itself is
+                                  // device-resident, sat_onepass.cu); bounds the 30-bit tag
   std::map<std::tuple<int, int, int, int>, SatGrid> sat_grids;
   std::map<std::tuple<int, int, int, int>, InterpLut> interp_luts;
   std::map<std::tuple<int, int, int, int>, ImgGrid> img_grids;
@@ -30,6 +32,20 @@ struct fov_ctx {
   const SatGrid *cur_sat_grid = nullptr;
   // device allocations handed out by fov_malloc and not yet freed: released with the context
   std::unordered_set<void *> allocations;
+  // CUDA-graph capture of a call sequence (fov_graph_*): while capturing nothing may allocate,
+  // clear or wait, so tables and scratch must exist already (run the sequence once beforehand)
+  bool capturing = false;
+  uint64_t capture_launches0 = 0;
+  uint32_t capture_sat0 = 0;
+  uint64_t scratch_generation = 0;  // bumped when the SAT scratch moves: captured graphs hold its address
+};
+
+struct fov_graph {
+  cudaGraph_t graph = nullptr;
+  cudaGraphExec_t exec = nullptr;
+  uint64_t kernels = 0;        // kernel launches per replay
+  uint32_t sat_launches = 0;   // one-pass SAT launches per replay (each consumes one epoch)
+  uint64_t scratch_generation = 0;
 };
 
 namespace fov {
@@ -104,6 +120,11 @@ int cuda_fail(fov_ctx *ctx, cudaError_t e, const char *what) {
 
 #define FOV_REQUIRE_CTX(ctx) \
   if (!(ctx)) return fail(nullptr, FOV_ERR_NO_CONTEXT, "fov360: not initialized with a CUDA context")
+#define FOV_NOT_WHILE_CAPTURING(ctx, what)                                                        \
+  if ((ctx)->capturing)                                                                           \
+    return fail(ctx, FOV_ERR_INVALID, std::string(what) +                                         \
+                ": not possible while a graph is being captured - run the same call sequence "   \
+                "once before fov_graph_begin_capture")
 #define FOV_CUDA(ctx, expr, what)                        \
   do {                                                   \
     cudaError_t e_ = (expr);                             \
@@ -152,6 +173,7 @@ int get_sat_grid(fov_ctx *ctx, int ow, int oh, int W, int H, const SatGrid **out
   auto key = std::make_tuple(ow, oh, W, H);
   auto it = ctx->sat_grids.find(key);
   if (it == ctx->sat_grids.end()) {
+    FOV_NOT_WHILE_CAPTURING(ctx, "sat grid creation");
     SatGrid g;
     g.ow = ow, g.oh = oh, g.W = W, g.H = H;
     build_sat_grid_edges(ow, oh, W, H, g.h_xedge, g.h_yedge);
@@ -168,6 +190,7 @@ int get_interp_lut(fov_ctx *ctx, int W, int H, int ow, int oh, const InterpLut *
   auto key = std::make_tuple(W, H, ow, oh);
   auto it = ctx->interp_luts.find(key);
   if (it == ctx->interp_luts.end()) {
+    FOV_NOT_WHILE_CAPTURING(ctx, "interp lut creation");
     InterpLut l;
     l.W = W, l.H = H, l.ow = ow, l.oh = oh;
     std::vector<InterpEntry> hx, hy;
@@ -186,6 +209,7 @@ int get_img_grid(fov_ctx *ctx, int ow, int oh, int W, int H, const ImgGrid **out
   auto key = std::make_tuple(ow, oh, W, H);
   auto it = ctx->img_grids.find(key);
   if (it == ctx->img_grids.end()) {
+    FOV_NOT_WHILE_CAPTURING(ctx, "img grid creation");
     ImgGrid g;
     g.ow = ow, g.oh = oh, g.W = W, g.H = H;
     build_img_grid_axes(ow, oh, W, H, g.h_xd, g.h_yd);
@@ -202,6 +226,7 @@ int get_lp_grid(fov_ctx *ctx, int ow, int oh, const LogpolarGrid **out) {
   auto key = std::make_tuple(ow, oh);
   auto it = ctx->lp_grids.find(key);
   if (it == ctx->lp_grids.end()) {
+    FOV_NOT_WHILE_CAPTURING(ctx, "logpolar grid creation");
     LogpolarGrid g;
     g.ow = ow, g.oh = oh;
     build_logpolar_axes(ow, oh, g.h_radius, g.h_cos, g.h_sin);
@@ -227,6 +252,8 @@ int get_lp_grid(fov_ctx *ctx, int ow, int oh, const LogpolarGrid **out) {
 int ensure_sat_scratch(fov_ctx *ctx, int n, int W, int H, bool onepass) {
   const size_t need = onepass ? sat_onepass_plan(n, W, H).bytes : sat_scratch_bytes(n, W, H);
   if (need <= ctx->sat_scratch.bytes) return FOV_OK;
+  FOV_NOT_WHILE_CAPTURING(ctx, "sat scratch allocation");
+  ++ctx->scratch_generation;
   if (ctx->sat_scratch.base) {
     FOV_CUDA(ctx, cudaStreamSynchronize(ctx->stream), "sat scratch resize");
     FOV_CUDA(ctx, cudaFree(ctx->sat_scratch.base), "sat scratch free");
@@ -458,6 +485,7 @@ int fov_sat_encode_batched(fov_ctx *ctx, int n, uint32_t *sat, size_t sat_stride
   if (rc) return rc;
   if (onepass) {
     if (ctx->sat_scratch_dirty || ctx->sat_epoch >= 0x3ffffff0u) {
+      FOV_NOT_WHILE_CAPTURING(ctx, "sat scratch clear");
       // Ticket counters and carry tags start from zero.  Alternating geometries or batch sizes need
       // no clear: tags carry a context-wide epoch, so units of other layouts are simply stale.
       FOV_CUDA(ctx, cudaMemsetAsync(ctx->sat_scratch.base, 0, ctx->sat_scratch.bytes, ctx->stream),
@@ -467,8 +495,9 @@ int fov_sat_encode_batched(fov_ctx *ctx, int n, uint32_t *sat, size_t sat_stride
     }
     FOV_CUDA(ctx,
              launch_sat_onepass(ctx->lc(), n, sat, sat_stride, src, src_stride, W, H, linesize,
-                                ctx->sat_scratch.base, ++ctx->sat_epoch),
+                                ctx->sat_scratch.base),
              "sat encode launch");
+    ++ctx->sat_epoch;
     return FOV_OK;
   }
   // Unaligned or 3-byte-pixel sources: the three-kernel reduce / carry / scan path.
@@ -519,14 +548,31 @@ int fov_sat_grid_export(fov_ctx *ctx, int16_t *host_grid, int ow, int oh, int W,
 }
 
 namespace {
+// Where the per-frame gaze comes from: a host array (copied into the launch parameters) or a device
+// array the kernels read themselves (graph-replayable launches).
+struct GazeSrc {
+  const float *host = nullptr;
+  const float *dev = nullptr;
+  bool ok() const { return host != nullptr || dev != nullptr; }
+  GazeBatch batch(int f0, int m) const {
+    GazeBatch gz;
+    memset(gz.xy, 0, sizeof(gz.xy));
+    if (dev)
+      gz.dev = dev + 2 * (size_t)f0;
+    else
+      memcpy(gz.xy, host + 2 * (size_t)f0, sizeof(float) * 2 * m);
+    return gz;
+  }
+};
+
 // sample_rect for n frames.  `src` (optional) are the RGB0 frames the SATs were built from by this
 // library in the same call sequence: the kernel may read 1x1 boxes from them (identical bits).
 int sample_rect_batched(fov_ctx *ctx, int n, uint8_t *out, size_t out_stride, int ow, int oh,
                         int out_linesize, const uint32_t *sat, size_t sat_stride, int W, int H,
-                        const float *gaze_xy, const uint8_t *src, size_t src_stride,
+                        const GazeSrc &gaze, const uint8_t *src, size_t src_stride,
                         int src_linesize) {
   FOV_REQUIRE_CTX(ctx);
-  if (n <= 0 || !out || !sat || !gaze_xy || ow <= 0 || oh <= 0 || out_linesize < 4 * ow ||
+  if (n <= 0 || !out || !sat || !gaze.ok() || ow <= 0 || oh <= 0 || out_linesize < 4 * ow ||
       (out_linesize % 4) != 0 || ((uintptr_t)out % 4) != 0 || (out_stride % 4) != 0 ||
       ((uintptr_t)sat % 4) != 0 || (sat_stride % 4) != 0 || W < 2 || H < 2)
     return fail(ctx, FOV_ERR_INVALID, "fov_sat_sample_rect: invalid arguments");
@@ -537,8 +583,7 @@ int sample_rect_batched(fov_ctx *ctx, int n, uint8_t *out, size_t out_stride, in
   ctx->cur_sat_grid = grid;
   for (int f0 = 0; f0 < n; f0 += kMaxBatchPerLaunch) {
     const int m = n - f0 < kMaxBatchPerLaunch ? n - f0 : kMaxBatchPerLaunch;
-    GazeBatch gz;
-    memcpy(gz.xy, gaze_xy + 2 * (size_t)f0, sizeof(float) * 2 * m);
+    const GazeBatch gz = gaze.batch(f0, m);
     FOV_CUDA(ctx,
              launch_sat_sample_rect(
                  ctx->lc(), m, out + (size_t)f0 * out_stride, out_stride, ow, oh, out_linesize,
@@ -550,13 +595,49 @@ int sample_rect_batched(fov_ctx *ctx, int n, uint8_t *out, size_t out_stride, in
   }
   return FOV_OK;
 }
+
+int interpolate_rect_batched(fov_ctx *ctx, int n, uint8_t *out, size_t out_stride, int W, int H,
+                             const uint8_t *red, size_t red_stride, int ow, int oh,
+                             const GazeSrc &gaze) {
+  FOV_REQUIRE_CTX(ctx);
+  if (n <= 0 || !out || !red || !gaze.ok() || ((uintptr_t)out % 4) != 0 || (out_stride % 4) != 0 ||
+      ((uintptr_t)red % 4) != 0 || (red_stride % 4) != 0)
+    return fail(ctx, FOV_ERR_INVALID, "fov_sat_interpolate_rect: invalid arguments");
+  DeviceGuard g(ctx);
+  const InterpLut *lut = nullptr;
+  int rc = get_interp_lut(ctx, W, H, ow, oh, &lut);
+  if (rc) return rc;
+  for (int f0 = 0; f0 < n; f0 += kMaxBatchPerLaunch) {
+    const int m = n - f0 < kMaxBatchPerLaunch ? n - f0 : kMaxBatchPerLaunch;
+    const GazeBatch gz = gaze.batch(f0, m);
+    FOV_CUDA(ctx,
+             launch_sat_interpolate_rect(ctx->lc(), m, out + (size_t)f0 * out_stride, out_stride,
+                                         W, H, red + (size_t)f0 * red_stride, red_stride, ow, oh,
+                                         lut->d_x, lut->d_y, gz),
+             "interpolate_rect launch");
+  }
+  return FOV_OK;
+}
+
+int encode_sample_batched(fov_ctx *ctx, int n, uint8_t *reduced, size_t red_stride, uint32_t *sat,
+                          size_t sat_stride, const uint8_t *src, size_t src_stride, int W, int H,
+                          int linesize, int ow, int oh, const GazeSrc &gaze) {
+  int rc = fov_sat_encode_batched(ctx, n, sat, sat_stride, src, src_stride, W, H, linesize);
+  if (rc) return rc;
+  // RGB0 frames with 4-byte aligned rows let sample_rect read its 1x1 boxes from the frame
+  static const bool no_hint = getenv("FOV360_SAMPLE_NO_SRC") != nullptr;
+  const bool hint = !no_hint && linesize / W == 4 && (linesize % 4) == 0 && ((uintptr_t)src % 4) == 0 &&
+                    (src_stride % 4) == 0;
+  return sample_rect_batched(ctx, n, reduced, red_stride, ow, oh, 4 * ow, sat, sat_stride, W, H,
+                             gaze, hint ? src : nullptr, src_stride, linesize);
+}
 }  // namespace
 
 int fov_sat_sample_rect_batched(fov_ctx *ctx, int n, uint8_t *out, size_t out_stride, int ow,
                                 int oh, int out_linesize, const uint32_t *sat, size_t sat_stride,
                                 int W, int H, const float *gaze_xy) {
   return sample_rect_batched(ctx, n, out, out_stride, ow, oh, out_linesize, sat, sat_stride, W, H,
-                             gaze_xy, nullptr, 0, 0);
+                             GazeSrc{gaze_xy, nullptr}, nullptr, 0, 0);
 }
 
 int fov_sat_sample_rect(fov_ctx *ctx, uint8_t *out, int ow, int oh, int out_linesize,
@@ -568,25 +649,8 @@ int fov_sat_sample_rect(fov_ctx *ctx, uint8_t *out, int ow, int oh, int out_line
 int fov_sat_interpolate_rect_batched(fov_ctx *ctx, int n, uint8_t *out, size_t out_stride, int W,
                                      int H, const uint8_t *red, size_t red_stride, int ow, int oh,
                                      const float *gaze_xy) {
-  FOV_REQUIRE_CTX(ctx);
-  if (n <= 0 || !out || !red || !gaze_xy || ((uintptr_t)out % 4) != 0 || (out_stride % 4) != 0 ||
-      ((uintptr_t)red % 4) != 0 || (red_stride % 4) != 0)
-    return fail(ctx, FOV_ERR_INVALID, "fov_sat_interpolate_rect: invalid arguments");
-  DeviceGuard g(ctx);
-  const InterpLut *lut = nullptr;
-  int rc = get_interp_lut(ctx, W, H, ow, oh, &lut);
-  if (rc) return rc;
-  for (int f0 = 0; f0 < n; f0 += kMaxBatchPerLaunch) {
-    const int m = n - f0 < kMaxBatchPerLaunch ? n - f0 : kMaxBatchPerLaunch;
-    GazeBatch gz;
-    memcpy(gz.xy, gaze_xy + 2 * (size_t)f0, sizeof(float) * 2 * m);
-    FOV_CUDA(ctx,
-             launch_sat_interpolate_rect(ctx->lc(), m, out + (size_t)f0 * out_stride, out_stride,
-                                         W, H, red + (size_t)f0 * red_stride, red_stride, ow, oh,
-                                         lut->d_x, lut->d_y, gz),
-             "interpolate_rect launch");
-  }
-  return FOV_OK;
+  return interpolate_rect_batched(ctx, n, out, out_stride, W, H, red, red_stride, ow, oh,
+                                  GazeSrc{gaze_xy, nullptr});
 }
 
 int fov_sat_interpolate_rect(fov_ctx *ctx, uint8_t *out, int W, int H, int out_linesize,
@@ -612,25 +676,113 @@ int fov_sat_encode_sample_batched(fov_ctx *ctx, int n, uint8_t *reduced, size_t 
                                   uint32_t *sat, size_t sat_stride, const uint8_t *src,
                                   size_t src_stride, int W, int H, int linesize, int ow, int oh,
                                   const float *gaze_xy) {
-  int rc = fov_sat_encode_batched(ctx, n, sat, sat_stride, src, src_stride, W, H, linesize);
-  if (rc) return rc;
-  // RGB0 frames with 4-byte aligned rows let sample_rect read its 1x1 boxes from the frame
-  static const bool no_hint = getenv("FOV360_SAMPLE_NO_SRC") != nullptr;
-  const bool hint = !no_hint && linesize / W == 4 && (linesize % 4) == 0 && ((uintptr_t)src % 4) == 0 &&
-                    (src_stride % 4) == 0;
-  return sample_rect_batched(ctx, n, reduced, red_stride, ow, oh, 4 * ow, sat, sat_stride, W, H,
-                             gaze_xy, hint ? src : nullptr, src_stride, linesize);
+  return encode_sample_batched(ctx, n, reduced, red_stride, sat, sat_stride, src, src_stride, W, H,
+                               linesize, ow, oh, GazeSrc{gaze_xy, nullptr});
 }
 
 int fov_sat_foveate_batched(fov_ctx *ctx, int n, uint8_t *full_out, size_t full_stride,
                             uint8_t *reduced, size_t red_stride, uint32_t *sat, size_t sat_stride,
                             const uint8_t *src, size_t src_stride, int W, int H, int linesize,
                             int ow, int oh, const float *gaze_xy) {
-  int rc = fov_sat_encode_sample_batched(ctx, n, reduced, red_stride, sat, sat_stride, src,
-                                         src_stride, W, H, linesize, ow, oh, gaze_xy);
+  const GazeSrc gaze{gaze_xy, nullptr};
+  int rc = encode_sample_batched(ctx, n, reduced, red_stride, sat, sat_stride, src, src_stride, W,
+                                 H, linesize, ow, oh, gaze);
   if (rc) return rc;
-  return fov_sat_interpolate_rect_batched(ctx, n, full_out, full_stride, W, H, reduced, red_stride,
-                                          ow, oh, gaze_xy);
+  return interpolate_rect_batched(ctx, n, full_out, full_stride, W, H, reduced, red_stride, ow, oh,
+                                  gaze);
+}
+
+// The same two sequences with the gaze in DEVICE memory (2n floats): the launches carry nothing that
+// changes from frame to frame, so they can be captured once and replayed (fov_graph_*).
+int fov_sat_encode_sample_batched_dev(fov_ctx *ctx, int n, uint8_t *reduced, size_t red_stride,
+                                      uint32_t *sat, size_t sat_stride, const uint8_t *src,
+                                      size_t src_stride, int W, int H, int linesize, int ow, int oh,
+                                      const float *gaze_dev) {
+  return encode_sample_batched(ctx, n, reduced, red_stride, sat, sat_stride, src, src_stride, W, H,
+                               linesize, ow, oh, GazeSrc{nullptr, gaze_dev});
+}
+
+int fov_sat_foveate_batched_dev(fov_ctx *ctx, int n, uint8_t *full_out, size_t full_stride,
+                                uint8_t *reduced, size_t red_stride, uint32_t *sat,
+                                size_t sat_stride, const uint8_t *src, size_t src_stride, int W,
+                                int H, int linesize, int ow, int oh, const float *gaze_dev) {
+  const GazeSrc gaze{nullptr, gaze_dev};
+  int rc = encode_sample_batched(ctx, n, reduced, red_stride, sat, sat_stride, src, src_stride, W,
+                                 H, linesize, ow, oh, gaze);
+  if (rc) return rc;
+  return interpolate_rect_batched(ctx, n, full_out, full_stride, W, H, reduced, red_stride, ow, oh,
+                                  gaze);
+}
+
+// ---- CUDA-graph capture of a call sequence (run_satlogrectilinear.cc:926-943 as one submission) --
+
+int fov_graph_begin_capture(fov_ctx *ctx) {
+  FOV_REQUIRE_CTX(ctx);
+  if (ctx->capturing) return fail(ctx, FOV_ERR_INVALID, "fov_graph_begin_capture: already capturing");
+  DeviceGuard g(ctx);
+  FOV_CUDA(ctx, cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal),
+           "fov_graph_begin_capture");
+  ctx->capturing = true;
+  ctx->capture_launches0 = ctx->launches;
+  ctx->capture_sat0 = ctx->sat_epoch;
+  return FOV_OK;
+}
+
+int fov_graph_end_capture(fov_ctx *ctx, fov_graph **out) {
+  FOV_REQUIRE_CTX(ctx);
+  if (!ctx->capturing) return fail(ctx, FOV_ERR_INVALID, "fov_graph_end_capture: not capturing");
+  DeviceGuard g(ctx);
+  ctx->capturing = false;
+  std::unique_ptr<fov_graph> gr(new fov_graph);
+  cudaError_t e = cudaStreamEndCapture(ctx->stream, &gr->graph);
+  if (e == cudaSuccess) e = cudaGraphInstantiate(&gr->exec, gr->graph, 0);
+  if (e != cudaSuccess) {
+    if (gr->graph) cudaGraphDestroy(gr->graph);
+    (void)cudaGetLastError();
+    if (out) *out = nullptr;
+    return cuda_fail(ctx, e, "fov_graph_end_capture");
+  }
+  gr->kernels = ctx->launches - ctx->capture_launches0;
+  gr->sat_launches = ctx->sat_epoch - ctx->capture_sat0;
+  gr->scratch_generation = ctx->scratch_generation;
+  // the captured launches did not run: give their counts back
+  ctx->launches = ctx->capture_launches0;
+  ctx->sat_epoch = ctx->capture_sat0;
+  if (!out) return fail(ctx, FOV_ERR_INVALID, "fov_graph_end_capture: null output pointer");
+  *out = gr.release();
+  return FOV_OK;
+}
+
+int fov_graph_launch(fov_ctx *ctx, fov_graph *graph) {
+  FOV_REQUIRE_CTX(ctx);
+  if (!graph || !graph->exec) return fail(ctx, FOV_ERR_INVALID, "fov_graph_launch: no graph");
+  if (ctx->capturing) return fail(ctx, FOV_ERR_INVALID, "fov_graph_launch: a capture is in progress");
+  if (graph->scratch_generation != ctx->scratch_generation)
+    return fail(ctx, FOV_ERR_INVALID,
+                "fov_graph_launch: the context's SAT scratch moved since the capture (a larger call "
+                "ran in between): capture the sequence again");
+  DeviceGuard g(ctx);
+  if (graph->sat_launches && (uint64_t)ctx->sat_epoch + graph->sat_launches >= 0x3ffffff0u) {
+    // the 30-bit epoch tag is about to wrap: clear the carry units and the device-side counter
+    FOV_CUDA(ctx, cudaMemsetAsync(ctx->sat_scratch.base, 0, ctx->sat_scratch.bytes, ctx->stream),
+             "sat scratch clear");
+    ctx->sat_epoch = 0;
+  }
+  FOV_CUDA(ctx, cudaGraphLaunch(graph->exec, ctx->stream), "fov_graph_launch");
+  ctx->launches += graph->kernels;
+  ctx->sat_epoch += graph->sat_launches;
+  return FOV_OK;
+}
+
+void fov_graph_destroy(fov_ctx *ctx, fov_graph *graph) {
+  if (!graph) return;
+  if (ctx) {
+    DeviceGuard g(ctx);
+    cudaStreamSynchronize(ctx->stream);
+  }
+  if (graph->exec) cudaGraphExecDestroy(graph->exec);
+  if (graph->graph) cudaGraphDestroy(graph->graph);
+  delete graph;
 }
 
 // ---- Projections ----------------------------------------------------------------------------

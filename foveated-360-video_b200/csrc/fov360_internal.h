@@ -174,6 +174,10 @@ cudaError_t launch_chained(void (*kernel)(KArgs...), dim3 grid, dim3 block, size
 
 struct GazeBatch {
   float xy[2 * kMaxBatchPerLaunch];
+  // When set, the kernels read the gaze of frame f from dev[2f], dev[2f+1] (device memory) instead
+  // of xy: nothing in the launch then depends on the gaze, so a captured CUDA graph replays with
+  // whatever the buffer holds at that time (fov_*_dev entry points).
+  const float *dev = nullptr;
 };
 
 // SAT build scratch: carry tables sized for (n, W, H); owned by the context.
@@ -196,7 +200,7 @@ bool sat_onepass_eligible(const uint32_t *sat, size_t sat_stride, const uint8_t 
                           size_t src_stride, int W, int H, int linesize);
 cudaError_t launch_sat_onepass(const LaunchCtx &lc, int n, uint32_t *sat, size_t sat_stride,
                                const uint8_t *src, size_t src_stride, int W, int H, int linesize,
-                               void *scratch, uint32_t epoch);
+                               void *scratch);
 
 cudaError_t launch_sat_sample_rect(const LaunchCtx &lc, int n, uint8_t *out, size_t out_stride, int ow,
                                    int oh, int out_linesize, const uint32_t *sat,

@@ -111,8 +111,8 @@ __global__ void __launch_bounds__(32 * kSampleWarps, FOV360_SAMPLE_MIN_CTAS)
   const int jb = blockIdx.y * kSampleWarps * kSampleRows;
   const int f = blockIdx.z;
   const int W = a.W, H = a.H, ow = a.ow, oh = a.oh;
-  const int cxp = gaze_px(g.xy[2 * f], W);
-  const int cyp = gaze_px(g.xy[2 * f + 1], H);
+  const int cxp = gaze_px(g.dev ? __ldg(g.dev + 2 * f) : g.xy[2 * f], W);
+  const int cyp = gaze_px(g.dev ? __ldg(g.dev + 2 * f + 1) : g.xy[2 * f + 1], H);
   const uint32_t row_words = (uint32_t)W * 3u;
 
   // ---- y edges of the CTA's rows: one thread per row ------------------------------------------
@@ -402,8 +402,8 @@ __global__ void __launch_bounds__(32 * kInterpWarps, FOV360_INTERP_MIN_CTAS)
   const int y0 = (blockIdx.y * kInterpWarps + warp) * kInterpRows;
   const int f = blockIdx.z;
   const int W = a.W, H = a.H, ow = a.ow, oh = a.oh;
-  const int cxp = gaze_px(g.xy[2 * f], W);
-  const int cyp = gaze_px(g.xy[2 * f + 1], H);
+  const int cxp = gaze_px(g.dev ? __ldg(g.dev + 2 * f) : g.xy[2 * f], W);
+  const int cyp = gaze_px(g.dev ? __ldg(g.dev + 2 * f + 1) : g.xy[2 * f + 1], H);
   const uint32_t *red = reinterpret_cast<const uint32_t *>(a.red + (size_t)f * a.red_stride);
 
   // Both table entries a lane needs - the x entry of its pixel slot and the y entry of its row - are

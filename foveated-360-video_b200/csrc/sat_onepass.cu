@@ -58,8 +58,8 @@ struct OnePassArgs {
   size_t src_stride, sat_stride;
   int W, H, linesize;
   int n, R, nb, ns, nsc;  // frames, band rows, bands, warp strips, CTA strips
-  uint32_t epoch, total_tiles;
-  uint32_t *counters;  // [0] ticket, [1] finished CTAs
+  uint32_t total_tiles;
+  uint32_t *counters;  // [0] ticket, [1] finished CTAs, [2] epoch of the last completed launch
   uint4 *rowagg;       // [tile][kMaxBandRows]  {r, g, b, epoch << 2 | kRow}: per-row sums of a CTA tile
   uint4 *colagg;       // [tile][NW][4][32]     {v0, v1, v2, epoch << 2 | state}: column carry
 #ifdef FOV360_SAT_TRACE
@@ -123,7 +123,7 @@ __device__ __forceinline__ uint4 load_row4(const uint8_t *row, int x0, int W, ui
 template <int MIN_CTAS, int kLoadDepth, int U>
 __global__ void __launch_bounds__(kMaxWarps * 32, MIN_CTAS) sat_onepass_kernel(const OnePassArgs a) {
   extern __shared__ __align__(128) uint8_t smem[];
-  __shared__ uint32_t s_ticket;
+  __shared__ uint32_t s_ticket, s_epoch;
   constexpr int kBufs = kStageBufs;
   const int NW = blockDim.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -136,9 +136,16 @@ __global__ void __launch_bounds__(kMaxWarps * 32, MIN_CTAS) sat_onepass_kernel(c
   pdl_trigger();
   if ((int)threadIdx.x < RS) s_left[threadIdx.x] = make_uint4(0, 0, 0, 0);
   pdl_wait();  // the frames (and the scratch of an earlier SAT build) are final from here on
-  if (threadIdx.x == 0) s_ticket = atomicAdd(&a.counters[0], 1u);
+  if (threadIdx.x == 0) {
+    s_ticket = atomicAdd(&a.counters[0], 1u);
+    // The launch epoch lives on the device: the last CTA of a launch stores the epoch it used, the
+    // next launch uses that + 1.  Nothing the host passes changes from launch to launch, so the
+    // launch can be replayed from a captured CUDA graph.
+    s_epoch = __ldcg(&a.counters[2]) + 1u;
+  }
   __syncthreads();
   const uint32_t tile = s_ticket;  // (band, frame, strip) order
+  const uint32_t epoch = s_epoch;
   FOV_TRACE(0);
   const int s = (int)(tile % (uint32_t)a.nsc);
   const int f = (int)((tile / (uint32_t)a.nsc) % (uint32_t)a.n);
@@ -208,7 +215,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32, MIN_CTAS) sat_onepass_kernel(c
       r0 += v.x, r1 += v.y, r2 += v.z;
     }
     if (s + 1 < a.nsc)  // somebody to the right will want it
-      st_unit(&a.rowagg[(size_t)tile * kMaxBandRows + r], r0, r1, r2, (a.epoch << 2) | kRow);
+      st_unit(&a.rowagg[(size_t)tile * kMaxBandRows + r], r0, r1, r2, (epoch << 2) | kRow);
   }
   FOV_TRACE(3);
 
@@ -223,7 +230,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32, MIN_CTAS) sat_onepass_kernel(c
         const int r = lane + 32 * h;
         if (r < rows) {
           uint4 v = ld_unit(pu + r);
-          while (v.w != ((a.epoch << 2) | kRow)) {
+          while (v.w != ((epoch << 2) | kRow)) {
             __nanosleep(20);
             v = ld_unit(pu + r);
           }
@@ -296,7 +303,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32, MIN_CTAS) sat_onepass_kernel(c
 #pragma unroll
         for (int k = 0; k < 4; ++k)
           st_unit(my_units + 32 * k, gsum[3 * k], gsum[3 * k + 1], gsum[3 * k + 2],
-                  (a.epoch << 2) | kAgg);
+                  (epoch << 2) | kAgg);
       }
       uint32_t open = in_x ? 0xfu : 0u;  // units still looking for an inclusive value
       uint32_t pc = col - col_step;
@@ -310,7 +317,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32, MIN_CTAS) sat_onepass_kernel(c
             if (pending & (1u << k)) u[k] = ld_unit(pu + 32 * k);
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
-            if ((pending & (1u << k)) && (u[k].w >> 2) == a.epoch) {
+            if ((pending & (1u << k)) && (u[k].w >> 2) == epoch) {
               acc[3 * k + 0] += u[k].x, acc[3 * k + 1] += u[k].y, acc[3 * k + 2] += u[k].z;
               pending &= ~(1u << k);
               if ((u[k].w & 3u) == kInc) open &= ~(1u << k);
@@ -325,7 +332,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32, MIN_CTAS) sat_onepass_kernel(c
 #pragma unroll
       for (int k = 0; k < 4; ++k)
         st_unit(my_units + 32 * k, acc[3 * k] + gsum[3 * k], acc[3 * k + 1] + gsum[3 * k + 1],
-                acc[3 * k + 2] + gsum[3 * k + 2], (a.epoch << 2) | kInc);
+                acc[3 * k + 2] + gsum[3 * k + 2], (epoch << 2) | kInc);
     }
     FOV_TRACE(5);
 
@@ -406,6 +413,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32, MIN_CTAS) sat_onepass_kernel(c
     if (atomicAdd(&a.counters[1], 1u) == a.total_tiles - 1) {
       a.counters[0] = 0;
       a.counters[1] = 0;
+      a.counters[2] = epoch;  // every other CTA has finished: nobody reads it before the next launch
     }
   }
 }
@@ -445,7 +453,7 @@ SatOnePassPlan sat_onepass_plan(int n, int W, int H) {
   p.off_rowagg = 256;
   p.off_colagg = p.off_rowagg + al(tiles * kMaxBandRows * 16);
   p.bytes = p.off_colagg + al(tiles * p.NW * 128 * 16);
-  // Every carry unit is tagged with the launch epoch, which only grows over the life of a context:
+  // Every carry unit is tagged with the launch epoch (kept in counters[2]), which only grows:
   // a unit left behind by any earlier launch, of this or another tile layout, can never carry the
   // current tag.  The scratch is zeroed when it is (re)allocated, after the three-kernel fallback
   // has used the same bytes, and when the epoch wraps.
@@ -464,7 +472,7 @@ bool sat_onepass_eligible(const uint32_t *sat, size_t sat_stride, const uint8_t 
 
 cudaError_t launch_sat_onepass(const LaunchCtx &lc, int n, uint32_t *sat, size_t sat_stride,
                                const uint8_t *src, size_t src_stride, int W, int H, int linesize,
-                               void *scratch, uint32_t epoch) {
+                               void *scratch) {
   const SatOnePassPlan p = sat_onepass_plan(n, W, H);
   uint8_t *base = static_cast<uint8_t *>(scratch);
   OnePassArgs a;
@@ -480,7 +488,6 @@ cudaError_t launch_sat_onepass(const LaunchCtx &lc, int n, uint32_t *sat, size_t
   a.nb = p.nb;
   a.ns = p.ns;
   a.nsc = p.nsc;
-  a.epoch = epoch;
   a.total_tiles = (uint32_t)((size_t)n * p.nb * p.nsc);
   a.counters = reinterpret_cast<uint32_t *>(base + p.off_counters);
   a.rowagg = reinterpret_cast<uint4 *>(base + p.off_rowagg);

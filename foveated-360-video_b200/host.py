@@ -133,6 +133,26 @@ class OpenCLManager:
         """clFlush + clFinish (video_server.cc:302-303)."""
         self._check(self.lib.fov_sync(self.ctx))
 
+    # -- CUDA-graph capture of a call sequence (no reference counterpart) ------------------
+    def BeginCapture(self) -> None:
+        self._check(self.lib.fov_graph_begin_capture(self.ctx))
+
+    def EndCapture(self) -> int:
+        g = C.c_void_p()
+        self._check(self.lib.fov_graph_end_capture(self.ctx, C.byref(g)))
+        return g.value
+
+    def LaunchGraph(self, graph: int) -> None:
+        self._check(self.lib.fov_graph_launch(self.ctx, graph))
+
+    def DestroyGraph(self, graph: int) -> None:
+        self.lib.fov_graph_destroy(self.ctx, graph)
+
+    def copy_to_device_async(self, dst, host: np.ndarray, dst_offset: int = 0) -> None:
+        """Stream-ordered host -> device copy; `host` must stay alive (and unchanged) until it ran."""
+        self._check(self.lib.fov_memcpy_h2d_async(self.ctx, _ptr(dst) + dst_offset, host.ctypes.data,
+                                                  host.nbytes))
+
     def close(self) -> None:
         if self.ctx:
             self.lib.fov_ctx_destroy(self.ctx)
@@ -245,6 +265,16 @@ def FoveateFramesGPU(m: OpenCLManager, n, full_out, full_stride, reduced, reduce
         m.ctx, n, _ptr(full_out), full_stride, _ptr(reduced), reduced_stride, _ptr(sat),
         sat_stride, _ptr(source), source_stride, width, height, source_linesize, ow, oh,
         g.ctypes.data_as(C.POINTER(C.c_float))))
+
+
+def FoveateFramesDeviceGazeGPU(m: OpenCLManager, n, full_out, full_stride, reduced, reduced_stride,
+                               sat, sat_stride, source, source_stride, width, height,
+                               source_linesize, ow, oh, gaze_dev):
+    """FoveateFramesGPU with the 2n gaze floats in a device buffer: capturable as a CUDA graph."""
+    m._check(m.lib.fov_sat_foveate_batched_dev(
+        m.ctx, n, _ptr(full_out), full_stride, _ptr(reduced), reduced_stride, _ptr(sat),
+        sat_stride, _ptr(source), source_stride, width, height, source_linesize, ow, oh,
+        _ptr(gaze_dev)))
 
 
 def EncodeSampleFramesGPU(m: OpenCLManager, n, reduced, reduced_stride, sat, sat_stride, source,

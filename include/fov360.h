@@ -168,6 +168,35 @@ int fov_sat_encode_sample_batched(fov_ctx *ctx, int n, uint8_t *reduced, size_t 
                                   int src_linesize, int red_width, int red_height,
                                   const float *gaze_xy);
 
+/* The two sequences above with the gaze array in DEVICE memory (2n floats, frame f at 2f, 2f+1):
+ * nothing in the launches changes from frame to frame - the gaze is read by the kernels, the SAT
+ * build keeps its launch epoch on the device - so a sequence can be captured once as a CUDA graph
+ * and replayed (the 3-stage pipeline as a single submission). */
+int fov_sat_encode_sample_batched_dev(fov_ctx *ctx, int n, uint8_t *reduced, size_t red_stride,
+                                      uint32_t *sat, size_t sat_stride, const uint8_t *src,
+                                      size_t src_stride, int src_width, int src_height,
+                                      int src_linesize, int red_width, int red_height,
+                                      const float *gaze_xy_dev);
+int fov_sat_foveate_batched_dev(fov_ctx *ctx, int n, uint8_t *full_out, size_t full_stride,
+                                uint8_t *reduced, size_t red_stride, uint32_t *sat,
+                                size_t sat_stride, const uint8_t *src, size_t src_stride,
+                                int src_width, int src_height, int src_linesize, int red_width,
+                                int red_height, const float *gaze_xy_dev);
+
+/* CUDA-graph capture of whatever is enqueued on the context between begin and end (kernels,
+ * fov_memset, fov_memcpy_*_async).  While capturing nothing may allocate, clear or wait: run the
+ * same sequence once before fov_graph_begin_capture so that tables and scratch exist (the call
+ * fails with FOV_ERR_INVALID and a message otherwise).  Use the *_dev entry points for anything
+ * whose gaze changes between replays and update the device array with fov_memcpy_h2d_async before
+ * fov_graph_launch.  A graph is tied to its context and to the buffers named at capture time; it
+ * is refused (FOV_ERR_INVALID) after the context's SAT scratch had to grow.  No reference
+ * counterpart (the OpenCL queue of the reference takes one clEnqueueNDRangeKernel per stage). */
+typedef struct fov_graph fov_graph;
+int fov_graph_begin_capture(fov_ctx *ctx);
+int fov_graph_end_capture(fov_ctx *ctx, fov_graph **graph);
+int fov_graph_launch(fov_ctx *ctx, fov_graph *graph);
+void fov_graph_destroy(fov_ctx *ctx, fov_graph *graph);
+
 /* ---- ImageSampler (image_sampler.h:57-65, 74-78, 84-91) --------------------------------- */
 
 /* ImageSampler::InitializeGrid (image_sampler.cc:170-202; create_grid_kernel,

@@ -618,6 +618,79 @@ def test_launch_chain_keeps_queue_order(dev, fov, oracle):
     assert np.array_equal(dev.m.copy_to_host(np.empty((H, W, 4), np.uint8), img), want_img)
 
 
+def test_captured_graph_replays_with_new_gaze(dev, fov, oracle):
+    """the 3-stage pipeline captured once as a CUDA graph (gaze in device
+    memory, SAT launch epoch on the device) and replayed with a different gaze every time - each
+    replay bit-identical to the oracle, SAT included, with nothing re-recorded in between."""
+    m = dev.m
+    W, H, n = 640, 360, 2
+    ow, oh = fov.reduced_dim(W), fov.reduced_dim(H)
+    frames = np.stack([O.lcg_frame(W, H, 70 + f) for f in range(n)])
+    src = m.upload(frames)
+    sat, red = m.Buffer(n * 12 * W * H), m.upload(np.zeros((n, oh, ow, 4), np.uint8))
+    full, gaze_dev = m.Buffer(n * 4 * W * H), m.Buffer(2 * n * 4)
+
+    def call():
+        fov.FoveateFramesDeviceGazeGPU(m, n, full, 4 * W * H, red, 4 * ow * oh, sat, 12 * W * H, src,
+                                       4 * W * H, W, H, 4 * W, ow, oh, gaze_dev)
+
+    m.copy_to_device(gaze_dev, np.asarray([(0.5, 0.5), (0.5, 0.5)], np.float32))
+    call()  # tables and scratch come into being outside the capture
+    m.Finish()
+    m.BeginCapture()
+    call()
+    graph = m.EndCapture()
+    want_sat = [oracle.sat_encode(frames[f]) for f in range(n)]
+    want_red = [np.zeros((oh, ow, 4), np.uint8) for _ in range(n)]
+    before = m.launch_count
+    sets = [[(0.65, 0.75), (0.02, 0.3)], [(1.0, 1.0), (0.0, 0.0)], [(0.31, 0.5), (0.98, 0.9)],
+            [(0.5, 0.5), (0.25, 0.999)]]
+    # the eager warm-up call wrote the reduced buffers once already (untouched pixels persist)
+    for f in range(n):
+        want_red[f] = oracle.sat_sample_rect(want_sat[f], ow, oh, 0.5, 0.5, out=want_red[f])
+    for gz in sets:
+        m.copy_to_device(gaze_dev, np.asarray(gz, np.float32))
+        m.memset(sat, 0, n * 12 * W * H)  # the replay really rebuilds the SAT
+        m.LaunchGraph(graph)
+        got_sat = m.copy_to_host(np.empty((n, H, W, 3), np.uint32), sat)
+        got_red = m.copy_to_host(np.empty((n, oh, ow, 4), np.uint8), red)
+        got_full = m.copy_to_host(np.empty((n, H, W, 4), np.uint8), full)
+        for f, (cx, cy) in enumerate(gz):
+            assert np.array_equal(got_sat[f], want_sat[f]), (gz, f)
+            want_red[f] = oracle.sat_sample_rect(want_sat[f], ow, oh, cx, cy, out=want_red[f])
+            assert np.array_equal(got_red[f], want_red[f]), (gz, f)
+            assert np.array_equal(got_full[f], oracle.sat_interpolate_rect(want_red[f], W, H, cx, cy))
+    assert m.launch_count - before == 3 * len(sets)  # three kernels per replay, counted
+    m.DestroyGraph(graph)
+    # eager calls still work after replays (the device-side epoch kept counting)
+    m.copy_to_device(gaze_dev, np.asarray(sets[0], np.float32))
+    call()
+    assert np.array_equal(m.copy_to_host(np.empty((n, H, W, 3), np.uint32), sat), np.stack(want_sat))
+
+
+def test_capture_needs_a_warm_call(fov):
+    """Nothing may allocate or wait while capturing: a cold context refuses, with a message, and
+    stays usable."""
+    m = fov.OpenCLManager(0)
+    m.InitializeContext()
+    W, H = 256, 128
+    ow, oh = fov.reduced_dim(W), fov.reduced_dim(H)
+    src = m.upload(O.lcg_frame(W, H, 1))
+    sat, red, full = m.Buffer(12 * W * H), m.Buffer(4 * ow * oh), m.Buffer(4 * W * H)
+    gaze_dev = m.upload(np.asarray([(0.5, 0.5)], np.float32))
+    m.Finish()
+    m.BeginCapture()
+    with pytest.raises(fov.FovError, match="graph is being captured"):
+        fov.FoveateFramesDeviceGazeGPU(m, 1, full, 4 * W * H, red, 4 * ow * oh, sat, 12 * W * H, src,
+                                       4 * W * H, W, H, 4 * W, ow, oh, gaze_dev)
+    m.DestroyGraph(m.EndCapture())  # an empty graph; the stream leaves capture mode
+    fov.FoveateFramesDeviceGazeGPU(m, 1, full, 4 * W * H, red, 4 * ow * oh, sat, 12 * W * H, src,
+                                   4 * W * H, W, H, 4 * W, ow, oh, gaze_dev)
+    got = m.copy_to_host(np.empty((H, W, 3), np.uint32), sat)
+    assert np.array_equal(got, O.port().sat_encode(O.lcg_frame(W, H, 1)))
+    m.close()
+
+
 # --------------------------------------------------------- directly against the reference ----
 @pytest.mark.skipif(not O.ref_available(), reason="oracle/_ref/libfovref.so not present")
 def test_8k_frame_against_reference_library(dev):

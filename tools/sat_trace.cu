@@ -35,12 +35,11 @@ int main(int argc, char **argv) {
   cudaEvent_t e0, e1;
   cudaEventCreate(&e0);
   cudaEventCreate(&e1);
-  uint32_t epoch = 0;
   for (int i = 0; i < 3; ++i)
-    launch_sat_onepass(lc, F, sat, (size_t)W * H * 12, src, (size_t)W * H * 4, W, H, W * 4, scratch, ++epoch);
+    launch_sat_onepass(lc, F, sat, (size_t)W * H * 12, src, (size_t)W * H * 4, W, H, W * 4, scratch);
   cudaEventRecord(e0, lc.stream);
   for (int i = 0; i < 10; ++i)
-    launch_sat_onepass(lc, F, sat, (size_t)W * H * 12, src, (size_t)W * H * 4, W, H, W * 4, scratch, ++epoch);
+    launch_sat_onepass(lc, F, sat, (size_t)W * H * 12, src, (size_t)W * H * 4, W, H, W * 4, scratch);
   cudaEventRecord(e1, lc.stream);
   cudaStreamSynchronize(lc.stream);
   float ms;
