@@ -100,7 +100,7 @@ struct __align__(16) SampleRow {
 #ifndef FOV360_SAMPLE_MIN_CTAS
 #define FOV360_SAMPLE_MIN_CTAS 6
 #endif
-template <int kSampleRows>
+template <int kSampleRows, bool kDevGaze>
 __global__ void __launch_bounds__(32 * kSampleWarps, FOV360_SAMPLE_MIN_CTAS)
     sat_sample_rect_kernel(const SampleArgs a,
                                                                             const GazeBatch g) {
@@ -111,8 +111,9 @@ __global__ void __launch_bounds__(32 * kSampleWarps, FOV360_SAMPLE_MIN_CTAS)
   const int jb = blockIdx.y * kSampleWarps * kSampleRows;
   const int f = blockIdx.z;
   const int W = a.W, H = a.H, ow = a.ow, oh = a.oh;
-  const int cxp = gaze_px(g.dev ? __ldg(g.dev + 2 * f) : g.xy[2 * f], W);
-  const int cyp = gaze_px(g.dev ? __ldg(g.dev + 2 * f + 1) : g.xy[2 * f + 1], H);
+  // kDevGaze is a template parameter: the run-time form of this choice cost the by-value path 1 %
+  const int cxp = gaze_px(kDevGaze ? __ldg(g.dev + 2 * f) : g.xy[2 * f], W);
+  const int cyp = gaze_px(kDevGaze ? __ldg(g.dev + 2 * f + 1) : g.xy[2 * f + 1], H);
   const uint32_t row_words = (uint32_t)W * 3u;
 
   // ---- y edges of the CTA's rows: one thread per row ------------------------------------------
@@ -386,7 +387,7 @@ __device__ __forceinline__ ulonglong2 sub_cols(const ulonglong2 n, const ulonglo
 //    colour is what the mixes select anyway, so V carries the sample's 4th byte along.
 //  * anything else (the warp straddles the edge of the 1:1 band, an exact hit that is not the
 //    selected tap, the +-W seam): generic row-by-row paths.
-template <int kInterpRows>
+template <int kInterpRows, bool kDevGaze>
 __global__ void __launch_bounds__(32 * kInterpWarps, FOV360_INTERP_MIN_CTAS)
     sat_interpolate_rect_kernel(const InterpArgs a, const GazeBatch g) {
   // staging area of a warp: kInterpChunk rows of V (34 slots each) in the periphery path, one row
@@ -402,8 +403,9 @@ __global__ void __launch_bounds__(32 * kInterpWarps, FOV360_INTERP_MIN_CTAS)
   const int y0 = (blockIdx.y * kInterpWarps + warp) * kInterpRows;
   const int f = blockIdx.z;
   const int W = a.W, H = a.H, ow = a.ow, oh = a.oh;
-  const int cxp = gaze_px(g.dev ? __ldg(g.dev + 2 * f) : g.xy[2 * f], W);
-  const int cyp = gaze_px(g.dev ? __ldg(g.dev + 2 * f + 1) : g.xy[2 * f + 1], H);
+  // kDevGaze is a template parameter: the run-time form of this choice cost the by-value path 1 %
+  const int cxp = gaze_px(kDevGaze ? __ldg(g.dev + 2 * f) : g.xy[2 * f], W);
+  const int cyp = gaze_px(kDevGaze ? __ldg(g.dev + 2 * f + 1) : g.xy[2 * f + 1], H);
   const uint32_t *red = reinterpret_cast<const uint32_t *>(a.red + (size_t)f * a.red_stride);
 
   // Both table entries a lane needs - the x entry of its pixel slot and the y entry of its row - are
@@ -917,7 +919,8 @@ cudaError_t launch_sat_sample_rect(const LaunchCtx &lc, int n, uint8_t *out, siz
                   (oh + kSampleWarps * kRows - 1) / (kSampleWarps * kRows), n),
       block(32, kSampleWarps);
   KernelScope ks(lc, "sat_sample_rect");
-  return launch_chained(sat_sample_rect_kernel<kRows>, grid, block, 0, lc.stream, a, gaze);
+  if (gaze.dev) return launch_chained(sat_sample_rect_kernel<kRows, true>, grid, block, 0, lc.stream, a, gaze);
+  return launch_chained(sat_sample_rect_kernel<kRows, false>, grid, block, 0, lc.stream, a, gaze);
 }
 
 cudaError_t launch_sat_interpolate_rect(const LaunchCtx &lc, int n, uint8_t *out, size_t out_stride,
@@ -949,9 +952,14 @@ cudaError_t launch_sat_interpolate_rect(const LaunchCtx &lc, int n, uint8_t *out
                   (H + kInterpWarps * rows - 1) / (kInterpWarps * rows), n),
       block(32, kInterpWarps);
   KernelScope ks(lc, "sat_interpolate_rect");
-  if (rows == 8) return launch_chained(sat_interpolate_rect_kernel<8>, grid, block, 0, lc.stream, a, gaze);
-  if (rows == 16) return launch_chained(sat_interpolate_rect_kernel<16>, grid, block, 0, lc.stream, a, gaze);
-  return launch_chained(sat_interpolate_rect_kernel<32>, grid, block, 0, lc.stream, a, gaze);
+  if (gaze.dev) {
+    if (rows == 8) return launch_chained(sat_interpolate_rect_kernel<8, true>, grid, block, 0, lc.stream, a, gaze);
+    if (rows == 16) return launch_chained(sat_interpolate_rect_kernel<16, true>, grid, block, 0, lc.stream, a, gaze);
+    return launch_chained(sat_interpolate_rect_kernel<32, true>, grid, block, 0, lc.stream, a, gaze);
+  }
+  if (rows == 8) return launch_chained(sat_interpolate_rect_kernel<8, false>, grid, block, 0, lc.stream, a, gaze);
+  if (rows == 16) return launch_chained(sat_interpolate_rect_kernel<16, false>, grid, block, 0, lc.stream, a, gaze);
+  return launch_chained(sat_interpolate_rect_kernel<32, false>, grid, block, 0, lc.stream, a, gaze);
 }
 
 cudaError_t launch_sat_interpolate_gnomonic(const LaunchCtx &lc, uint8_t *out, int tw, int th,
