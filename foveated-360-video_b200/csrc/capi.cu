@@ -762,10 +762,13 @@ int fov_graph_launch(fov_ctx *ctx, fov_graph *graph) {
                 "fov_graph_launch: the context's SAT scratch moved since the capture (a larger call "
                 "ran in between): capture the sequence again");
   DeviceGuard g(ctx);
-  if (graph->sat_launches && (uint64_t)ctx->sat_epoch + graph->sat_launches >= 0x3ffffff0u) {
-    // the 30-bit epoch tag is about to wrap: clear the carry units and the device-side counter
+  if (graph->sat_launches &&
+      (ctx->sat_scratch_dirty || (uint64_t)ctx->sat_epoch + graph->sat_launches >= 0x3ffffff0u)) {
+    // the three-kernel fallback used the scratch since the capture, or the 30-bit epoch tag is about
+    // to wrap: clear the carry units and the device-side counter before the replay
     FOV_CUDA(ctx, cudaMemsetAsync(ctx->sat_scratch.base, 0, ctx->sat_scratch.bytes, ctx->stream),
              "sat scratch clear");
+    ctx->sat_scratch_dirty = false;
     ctx->sat_epoch = 0;
   }
   FOV_CUDA(ctx, cudaGraphLaunch(graph->exec, ctx->stream), "fov_graph_launch");

@@ -634,6 +634,9 @@ def test_captured_graph_replays_with_new_gaze(dev, fov, oracle):
         fov.FoveateFramesDeviceGazeGPU(m, n, full, 4 * W * H, red, 4 * ow * oh, sat, 12 * W * H, src,
                                        4 * W * H, W, H, 4 * W, ow, oh, gaze_dev)
 
+    rgb = np.ascontiguousarray(frames[0][..., :3])
+    src24, sat24 = m.upload(rgb), m.Buffer(12 * W * H)
+    dev.enc.EncodeFrameGPU(sat24, src24, W, H, 3 * W)  # sizes the scratch for the fallback path, too
     m.copy_to_device(gaze_dev, np.asarray([(0.5, 0.5), (0.5, 0.5)], np.float32))
     call()  # tables and scratch come into being outside the capture
     m.Finish()
@@ -661,6 +664,13 @@ def test_captured_graph_replays_with_new_gaze(dev, fov, oracle):
             assert np.array_equal(got_red[f], want_red[f]), (gz, f)
             assert np.array_equal(got_full[f], oracle.sat_interpolate_rect(want_red[f], W, H, cx, cy))
     assert m.launch_count - before == 3 * len(sets)  # three kernels per replay, counted
+    # a three-kernel SAT build (3-byte pixels) borrows the same scratch; the next replay must not
+    # mistake what it left there for carry units
+    dev.enc.EncodeFrameGPU(sat24, src24, W, H, 3 * W)
+    assert np.array_equal(m.copy_to_host(np.empty((H, W, 3), np.uint32), sat24), want_sat[0])
+    m.memset(sat, 0, n * 12 * W * H)
+    m.LaunchGraph(graph)
+    assert np.array_equal(m.copy_to_host(np.empty((n, H, W, 3), np.uint32), sat), np.stack(want_sat))
     m.DestroyGraph(graph)
     # eager calls still work after replays (the device-side epoch kept counting)
     m.copy_to_device(gaze_dev, np.asarray(sets[0], np.float32))
