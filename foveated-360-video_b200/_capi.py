@@ -80,6 +80,7 @@ PROTOTYPES = {
     "fov_yuv420p_to_rgb0_batched": (_i, [_vp, _i, _vp, _sz, _i, _vp, _sz, _i, _vp, _vp, _sz, _i,
                                          _i, _i]),
     "fov_nv12_to_rgb0_batched": (_i, [_vp, _i, _vp, _sz, _i, _vp, _sz, _i, _vp, _sz, _i, _i, _i]),
+    "fov_debug_bounds_violations": (_i, [_vp, C.POINTER(C.c_uint), C.POINTER(C.c_uint)]),
     "fov_reduced_dim": (_i, [_i]),
 }
 

@@ -26,7 +26,7 @@ LIB_PATH = os.path.join(HERE, "libfov360.so")
 
 SOURCES = ["capi.cu", "sat_encode.cu", "sat_onepass.cu", "sat_decode.cu", "image_sampler.cu",
            "projections.cu", "color_convert.cu", "luts.cc"]
-HEADERS = [os.path.join(CSRC, "fov360_internal.h"), os.path.join(CSRC, "sat_common.cuh"),
+HEADERS = [os.path.join(CSRC, "fov360_internal.h"), os.path.join(CSRC, "sat_common.cuh"), os.path.join(CSRC, "bounds_check.cuh"),
            os.path.join(CSRC, "projection_common.cuh"), os.path.join(CSRC, "pixel_math.cuh"),
            os.path.join(INCLUDE, "fov360.h")]
 
@@ -111,6 +111,44 @@ def _build_locked(nvcc: str, srcs: list[str], digest: str, force: bool, verbose:
         fh.write(digest + "\n")
     os.replace(MANIFEST + ".tmp", MANIFEST)
     return LIB_PATH
+
+
+CHECK_LIB_PATH = os.path.join(HERE, "libfov360_check.so")
+CHECK_MANIFEST = os.path.join(HERE, "libfov360_check.manifest")
+
+
+def build_check(force: bool = False) -> str:
+    """The same library with -DFOV360_BOUNDS_CHECK (csrc/bounds_check.cuh): test infrastructure for
+    tests/test_gpu_bounds.py, never loaded unless FOV360_LIB points at it."""
+    srcs = [os.path.join(CSRC, s) for s in SOURCES]
+    digest = _digest(srcs + HEADERS) + "+check"
+    if not force and os.path.exists(CHECK_LIB_PATH) and os.path.exists(CHECK_MANIFEST):
+        with open(CHECK_MANIFEST) as fh:
+            if fh.read().strip() == digest:
+                return CHECK_LIB_PATH
+    nvcc = nvcc_path()
+    obj_dir = os.path.join(OBJ_DIR, "check")
+    os.makedirs(obj_dir, exist_ok=True)
+    with open(os.path.join(OBJ_DIR, ".lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        objs = [os.path.join(obj_dir, os.path.splitext(s)[0] + ".o") for s in SOURCES]
+
+        def one(src, obj):
+            r = subprocess.run([nvcc, *NVCC_FLAGS, "-DFOV360_BOUNDS_CHECK", "-c", src, "-o", obj],
+                               capture_output=True, text=True)
+            if r.returncode:
+                sys.stderr.write(r.stdout + r.stderr)
+                raise RuntimeError("nvcc failed for " + src)
+
+        with cf.ThreadPoolExecutor(max_workers=max(1, min(len(srcs), os.cpu_count() or 1))) as ex:
+            for fut in [ex.submit(one, s, o) for s, o in zip(srcs, objs)]:
+                fut.result()
+        tmp = CHECK_LIB_PATH + ".tmp%d" % os.getpid()
+        subprocess.check_call([nvcc, *ARCH, "-shared", "-cudart", "static", "-o", tmp, *objs])
+        os.replace(tmp, CHECK_LIB_PATH)
+        with open(CHECK_MANIFEST, "w") as fh:
+            fh.write(digest + "\n")
+    return CHECK_LIB_PATH
 
 
 if __name__ == "__main__":

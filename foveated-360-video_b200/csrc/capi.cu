@@ -1067,6 +1067,22 @@ int fov_nv12_to_rgb0_batched(fov_ctx *ctx, int n, uint8_t *dst, size_t dst_strid
                      y_stride, y_linesize, uv, uv_linesize, nullptr, 0, uv_stride, width, height);
 }
 
+int fov_debug_bounds_violations(fov_ctx *ctx, unsigned *count, unsigned *first_site) {
+  FOV_REQUIRE_CTX(ctx);
+  DeviceGuard g(ctx);
+  FOV_CUDA(ctx, cudaStreamSynchronize(ctx->stream), "fov_debug_bounds_violations");
+  unsigned a[2] = {0, 0}, b[2] = {0, 0};
+  bounds_read_image_sampler(a);
+  bounds_read_sat_decode(b);
+  if (count) *count = a[0] + b[0];
+  if (first_site) *first_site = a[0] ? a[1] : b[1];
+#ifdef FOV360_BOUNDS_CHECK
+  return 1;  // a checking build
+#else
+  return FOV_OK;
+#endif
+}
+
 int fov_reduced_dim(int full_dim) {
   // 16 * ceil(dim / 1.8 / 16), run_satlogrectilinear.cc:113-114
   return 16 * (int)std::ceil(full_dim / 1.8 / 16);

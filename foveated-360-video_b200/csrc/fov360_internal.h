@@ -170,6 +170,11 @@ cudaError_t launch_chained(void (*kernel)(KArgs...), dim3 grid, dim3 block, size
 }
 #endif
 
+// Index-check counters of the gather kernels (bounds_check.cuh; zero unless the library was built
+// with -DFOV360_BOUNDS_CHECK): {violations, site of the first one} per translation unit.
+void bounds_read_image_sampler(unsigned out[2]);
+void bounds_read_sat_decode(unsigned out[2]);
+
 // ---- kernel launchers (one per .cu) ----------------------------------------------------------
 
 struct GazeBatch {

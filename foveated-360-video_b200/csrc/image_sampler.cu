@@ -7,6 +7,7 @@
 // (image_sampler_interpolate_kernel.cl:1-81).  The 2-D int16 grids of the reference are
 // replaced by their separable 1-D factors (luts.cc); the grid value is re-formed in
 // registers, which removes a 4 B/pixel table read from both samplers.
+#include "bounds_check.cuh"
 #include "fov360_internal.h"
 #include "pixel_math.cuh"
 
@@ -52,6 +53,7 @@ __global__ void __launch_bounds__(256) img_sample_rect_kernel(const GatherArgs a
   const int i = blockIdx.x * 32 + threadIdx.x;
   const int j0 = (blockIdx.y * 8 + threadIdx.y) * kGatherRows;
   if (i >= a.ow || j0 >= a.oh) return;
+  FOV_CHECK(i, a.ow, 101);
   int x = gaze_plus(a.cx, a.W, xd[i]);
   if (x >= a.W)  // :29-33
     x -= a.W;
@@ -67,6 +69,7 @@ __global__ void __launch_bounds__(256) img_sample_rect_kernel(const GatherArgs a
     for (int r = 0; r < kGatherRows; ++r) {
       const int y = gaze_plus(a.cy, a.H, yd[min(j0 + r, a.oh - 1)]);
       on[r] = j0 + r < a.oh && y >= 0 && y < a.H;  // :35-43
+      if (on[r]) FOV_CHECK((size_t)y * a.src_linesize + (size_t)x * a.sbpp + 3, (size_t)a.H * a.src_linesize, 102);
       v[r] = on[r] ? __ldg(reinterpret_cast<const uint32_t *>(scol + (size_t)y * a.src_linesize)) : 0u;
     }
 #pragma unroll
@@ -118,6 +121,9 @@ __global__ void __launch_bounds__(256) img_sample_logpolar_kernel(
     x = mod_width(x + W10, a.W, rcpW);  // :73
     y = clampi(y, 0, a.H - 1);
     on[k] = j0 + k < a.oh && x >= 0;  // :76-77 (x stays negative only for x < -10 W)
+    FOV_CHECK(j, a.oh, 111);
+    if (on[k]) FOV_CHECK(x, a.W, 112);
+    if (on[k]) FOV_CHECK((size_t)y * a.src_linesize + (size_t)x * a.sbpp + (a.word_ok ? 3 : 2), (size_t)a.H * a.src_linesize, 113);
     sp[k] = a.src + (size_t)y * a.src_linesize + (size_t)max(x, 0) * a.sbpp;
   }
   if (a.word_ok) {
@@ -217,6 +223,8 @@ __device__ __noinline__ float logpolar_jf_exact(int dx, int dy, int oh) {
 
 __device__ __forceinline__ bool logpolar_hits(const LpInterpArgs &a, int i, int j, double cxw,
                                               double cyh, int x, int y) {
+  FOV_CHECK(i, a.ow, 122);
+  FOV_CHECK(j, a.oh, 123);
   const double rad = __ldg(a.radius + i);
   const double2 cs = __ldg(a.dir + j);
   const int calc_x = __double2int_rz(__dadd_rn(cxw, __dmul_rn(rad, cs.x)));  // :46-48
@@ -278,6 +286,7 @@ __global__ void __launch_bounds__(kLpThreads, FOV360_LP_MIN_CTAS) img_interpolat
       const int d2 = dx2 + rw.dy2;
       centre[k] = d2 == 0;
       const float d2f = fmaxf(__fmaf_rn(rw.ady, rw.ady, fdx2), 1.0f);
+      FOV_CHECK((int)(__float_as_uint(d2f) >> 16) - (127 << 7), kLnExponents * 128, 121);
       const double2 te = __ldg(a.lntab + ((int)(__float_as_uint(d2f) >> 16) - (127 << 7)));
       const double dd = __hiloint2double(0x43300000, d2) - 4503599627370496.0;  // (double)d2
       const double rr = fma(dd, te.x, -1.0);
@@ -326,10 +335,13 @@ __global__ void __launch_bounds__(kLpThreads, FOV360_LP_MIN_CTAS) img_interpolat
       int ii = __float2int_rz(fi);
       int i = ii + (ir[k] >= 0.5f ? 1 : 0);  // :34
       if (fabsf(jr[k] - 0.5f) < a.zone || centre[k]) {
-        // round(j_f) is not certain: it matters only if a candidate is an exact hit
-        const bool ha = logpolar_hits(a, i, jj, cxw, cyh, x, yy[k]);  // j_f < oh
-        const bool hb = logpolar_hits(a, i, min(jj + 1, oh - 1), cxw, cyh, x, yy[k]);
-        if (ha || hb || centre[k]) {
+        // round(j_f) is not certain: it matters only if a candidate is an exact hit.  (At the gaze
+        // pixel itself d2 = 0 and the logarithm above is meaningless: its index is not used.)
+        bool exact = centre[k];
+        if (!exact)
+          exact = logpolar_hits(a, i, jj, cxw, cyh, x, yy[k]) ||  // j_f < oh
+                  logpolar_hits(a, i, min(jj + 1, oh - 1), cxw, cyh, x, yy[k]);
+        if (exact) {
           if (centre[k]) ir[k] = 0.0f, ii = 0, i = 0;  // i_f = 0 at the gaze pixel itself (:28-29)
           fj = floorf(j_f[k] = logpolar_jf_exact(dx, yy[k] - cyp, oh));
           jr[k] = __fsub_rn(j_f[k], fj);
@@ -349,6 +361,10 @@ __global__ void __launch_bounds__(kLpThreads, FOV360_LP_MIN_CTAS) img_interpolat
     uint32_t tl[2], tr[2], bl[2], br[2];
 #pragma unroll
     for (int k = 0; k < 2; ++k) {
+      FOV_CHECK(tj0[k], oh, 124);
+      FOV_CHECK(tj1[k], oh, 125);
+      FOV_CHECK(ti0[k], ow, 126);
+      FOV_CHECK(ti1[k], ow, 127);
       const uint32_t ra = (uint32_t)(tj0[k] * ow), rb = (uint32_t)(tj1[k] * ow);  // ow * oh < 2^31
       tl[k] = __ldg(a.red + (ra + (uint32_t)ti0[k]));
       tr[k] = __ldg(a.red + (ra + (uint32_t)ti1[k]));
@@ -472,6 +488,10 @@ __global__ void __launch_bounds__(32 * kBlurWarps, 6) img_logpolar_blur4_kernel(
     uint32_t p[6];  // left halo, the lane's 4 pixels, right halo
   };
   auto load_row = [&](int j) {
+    FOV_CHECK(j, oh, 131);
+    FOV_CHECK(gc * 4 + 3, ow, 132);
+    FOV_CHECK(il, ow, 133);
+    FOV_CHECK(irr, ow, 134);
     const uint32_t *row = src + (size_t)j * ow;
     const uint4 raw = __ldg(reinterpret_cast<const uint4 *>(row) + gc);
     Raw6 r;
@@ -553,6 +573,8 @@ GatherArgs make_gather(uint8_t *out, int ow, int oh, int out_linesize, const uin
 }
 
 }  // namespace
+
+FOV_DEFINE_BOUNDS_READER(bounds_read_image_sampler)
 
 cudaError_t launch_img_sample_rect(const LaunchCtx &lc, uint8_t *out, int ow, int oh, int out_linesize,
                                    const uint8_t *src, int W, int H, int src_linesize,

@@ -8,6 +8,7 @@
 // tables (luts.cc), so the kernels are integer/gather work bounded by HBM/L2 bandwidth.
 #include <cstdlib>
 
+#include "bounds_check.cuh"
 #include "fov360_internal.h"
 #include "pixel_math.cuh"
 #include "projection_common.cuh"
@@ -126,6 +127,8 @@ __global__ void __launch_bounds__(32 * kSampleWarps, FOV360_SAMPLE_MIN_CTAS)
       const bool y_in = (y1 >= 0 && y1 < H) || (y0 >= 0 && y0 < H);  // :199-200
       const int py = clampi(y1, 1, H - 1);                            // :202, :204
       const int my = clampi(y0, 0, py - 1);
+      FOV_CHECK(py, H, 201);
+      FOV_CHECK(my, H, 202);
       SampleRow d;
       d.top_off = (uint32_t)my * row_words;
       d.bot_off = (uint32_t)py * row_words;
@@ -159,6 +162,9 @@ __global__ void __launch_bounds__(32 * kSampleWarps, FOV360_SAMPLE_MIN_CTAS)
   const bool share = lane < 31 && i + 1 < ow && px == mx_next;
   const bool own_right = has_px && !share;
   const bool live = has_px && x_in;
+  FOV_CHECK(ic + 1, ow + 1, 203);
+  FOV_CHECK(px, W, 204);
+  FOV_CHECK(mx, W, 205);
   const uint32_t colL = (uint32_t)mx * 3u, colR = (uint32_t)px * 3u;
   const uint32_t dx = (uint32_t)(px - mx);
 
@@ -429,7 +435,11 @@ __global__ void __launch_bounds__(32 * kInterpWarps, FOV360_INTERP_MIN_CTAS)
       wrapped = true;
     }
     const int dx = clampi(x - cxp, -W, W);
+    FOV_CHECK(dx + W, 2 * W + 1, 211);
     const AxisSel sx = resolve_axis(load_entry(a.lx + (dx + W)), cxp, W, ow, wrapped);
+    FOV_CHECK(sx.lo, ow, 212);
+    FOV_CHECK(sx.hi, ow, 213);
+    FOV_CHECK(sx.exact_idx, ow, 214);
     xsel[warp][lane] = make_int4(sx.lo, sx.hi, __float_as_int(sx.ratio), sx.exact ? sx.exact_idx : -1);
   }
   __syncthreads();
@@ -471,6 +481,9 @@ __global__ void __launch_bounds__(32 * kInterpWarps, FOV360_INTERP_MIN_CTAS)
   // ---- y axis: one lane per row --------------------------------------------------------------
   {
     const AxisSel sy = resolve_axis(ey, cyp, H, oh, false);
+    FOV_CHECK(sy.lo, oh, 215);
+    FOV_CHECK(sy.hi, oh, 216);
+    FOV_CHECK(sy.exact_idx, oh, 217);
     const bool deg = sy.ratio == 0.0f || sy.ratio == 1.0f;
     const int sel = sy.ratio == 1.0f ? sy.hi : sy.lo;
     const int rlo = deg ? sel : sy.lo, rhi = deg ? sel : sy.hi;
@@ -890,6 +903,8 @@ __global__ void __launch_bounds__(256) sat_decode_kernel(uint8_t *out, int out_l
 }
 
 }  // namespace
+
+FOV_DEFINE_BOUNDS_READER(bounds_read_sat_decode)
 
 cudaError_t launch_sat_sample_rect(const LaunchCtx &lc, int n, uint8_t *out, size_t out_stride, int ow,
                                    int oh, int out_linesize, const uint32_t *sat,

@@ -306,6 +306,12 @@ int fov_nv12_to_rgb0_batched(fov_ctx *ctx, int n, uint8_t *dst, size_t dst_strid
  * 16*ceil(dim/1.8/16) (run_satlogrectilinear.cc:113-114). */
 int fov_reduced_dim(int full_dim);
 
+/* Development aid (no reference counterpart): libraries built with -DFOV360_BOUNDS_CHECK compare
+ * every table index and gathered coordinate of the sampling / warp kernels with its limit; this
+ * returns the number of violations since the library was loaded and the site of the first one.
+ * Returns 1 from a checking build, 0 (and a count of 0) from a normal one. */
+int fov_debug_bounds_violations(fov_ctx *ctx, unsigned *count, unsigned *first_site);
+
 #ifdef __cplusplus
 }
 #endif

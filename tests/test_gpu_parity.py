@@ -559,6 +559,26 @@ def test_image_sampler_vs_oracle(dev, oracle, W, H, ow, oh):
         assert np.array_equal(got[..., 3], want[..., 3]), (cx, cy)  # exact hits copy the 4th byte
 
 
+def test_image_sampler_three_byte_pixels(dev, oracle):
+    """The gathers derive the pixel stride from linesize / width like the reference
+    (image_sampler_sample_rect_kernel.cl:12-13, image_sampler_sample_logpolar_kernel.cl:49-50):
+    packed RGB24 sources and targets take the byte-wise path."""
+    W, H, ow, oh = 320, 200, 176, 112
+    frame = np.ascontiguousarray(O.lcg_frame(W, H, 9)[..., :3])
+    src = dev.m.upload(frame)
+    for cx, cy in [(0.5, 0.5), (0.02, 0.9), (1.0, 0.0)]:
+        for target_bpp in (3, 4):
+            pre = np.full((oh, ow, target_bpp), 0xAB, np.uint8)
+            out = dev.m.upload(pre)
+            dev.img.SampleFrameRectGPU(out, ow, oh, target_bpp * ow, src, W, H, 3 * W, cx, cy)
+            assert np.array_equal(dev.m.copy_to_host(pre.copy(), out),
+                                  oracle.img_sample_rect(frame, ow, oh, cx, cy, out=pre.copy()))
+            out = dev.m.upload(pre)
+            dev.img.SampleFrameLogPolarGPU(out, ow, oh, target_bpp * ow, src, W, H, 3 * W, cx, cy)
+            assert np.array_equal(dev.m.copy_to_host(pre.copy(), out),
+                                  oracle.img_sample_logpolar(frame, ow, oh, cx, cy, out=pre.copy()))
+
+
 def test_encode_sample_batched_equals_separate_calls(dev, fov, oracle):
     """fov_sat_encode_sample_batched (the server's two stages, video_server.cc:300-338) against the
     single-frame calls and the oracle: SATs and reduced buffers bit-identical, per-frame gaze."""
@@ -676,6 +696,31 @@ def test_captured_graph_replays_with_new_gaze(dev, fov, oracle):
     m.copy_to_device(gaze_dev, np.asarray(sets[0], np.float32))
     call()
     assert np.array_equal(m.copy_to_host(np.empty((n, H, W, 3), np.uint32), sat), np.stack(want_sat))
+
+
+def test_device_gaze_batch_larger_than_one_launch(dev, fov, oracle):
+    """More frames than one launch carries gaze slots for (64): the device gaze pointer advances
+    with the chunk, like the host array does."""
+    m = dev.m
+    W, H, n = 96, 64, 70
+    ow, oh = fov.reduced_dim(W), fov.reduced_dim(H)
+    rng = np.random.default_rng(5)
+    frames = rng.integers(0, 256, size=(n, H, W, 4), dtype=np.uint8)
+    frames[..., 3] = 0
+    gaze = rng.random((n, 2)).astype(np.float32)
+    src, gaze_dev = m.upload(frames), m.upload(gaze)
+    sat, red = m.Buffer(n * 12 * W * H), m.upload(np.zeros((n, oh, ow, 4), np.uint8))
+    full = m.Buffer(n * 4 * W * H)
+    fov.FoveateFramesDeviceGazeGPU(m, n, full, 4 * W * H, red, 4 * ow * oh, sat, 12 * W * H, src,
+                                   4 * W * H, W, H, 4 * W, ow, oh, gaze_dev)
+    got_red = m.copy_to_host(np.empty((n, oh, ow, 4), np.uint8), red)
+    got_full = m.copy_to_host(np.empty((n, H, W, 4), np.uint8), full)
+    for f in (0, 1, 63, 64, 65, 69):
+        want_red = oracle.sat_sample_rect(oracle.sat_encode(frames[f]), ow, oh, float(gaze[f, 0]),
+                                          float(gaze[f, 1]))
+        assert np.array_equal(got_red[f], want_red), f
+        assert np.array_equal(got_full[f], oracle.sat_interpolate_rect(
+            want_red, W, H, float(gaze[f, 0]), float(gaze[f, 1]))), f
 
 
 def test_capture_needs_a_warm_call(fov):
