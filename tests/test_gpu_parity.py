@@ -217,6 +217,29 @@ def test_sat_alternating_layouts_and_batches(dev, oracle):
             sat.free()
 
 
+def test_sat_back_to_back_launches_share_scratch(dev, oracle):
+    """Consecutive SAT builds of different tile layouts queued with NO synchronisation in between:
+    they share the context's scratch (ticket counters, device-side epoch, carry units) and are
+    launched with programmatic dependent launch, so launch k + 1 becomes resident while launch k
+    drains.  Every table is checked after a single wait at the end."""
+    rng = np.random.default_rng(10)
+    cases = [(512, 96, 2), (1280, 720, 1), (260, 52, 3), (1920, 1080, 1)] * 3
+    work = []
+    for W, H, n in cases:
+        frames = rng.integers(0, 256, (n, H, W, 4), dtype=np.uint8)
+        work.append((W, H, n, frames, dev.m.upload(frames), dev.m.Buffer(n * W * H * 12)))
+    dev.m.Finish()
+    for W, H, n, frames, src, sat in work:  # nothing waits inside this loop
+        dev.enc.EncodeFramesGPU(n, sat, W * H * 12, src, W * H * 4, W, H, 4 * W)
+    dev.m.Finish()
+    for k, (W, H, n, frames, src, sat) in enumerate(work):
+        got = dev.m.copy_to_host(np.empty((n, H, W, 3), np.uint32), sat)
+        for f in range(n):
+            assert np.array_equal(got[f], oracle.sat_encode(frames[f])), (k, W, H, n, f)
+        src.free()
+        sat.free()
+
+
 # ----------------------------------------------------------------------- sample / interpolate ----
 @pytest.mark.parametrize("W,H,ow,oh", [(1920, 1080, 1072, 608), (640, 360, 368, 208),
                                        (1000, 500, 300, 200), (333, 211, 100, 77)])
