@@ -4,7 +4,7 @@
  * This is the drop-in boundary for the per-frame foveation hot path of
  * AugmentariumLab/foveated-360-video.  It replaces the reference's OpenCL layer
  * (src/opencl_manager.{h,cc} + cl::Buffer / cl::copy at the call sites) and is what
- * the C++ classes in include/fov360/*.h (SATEncoder / SATDecoder / ImageSampler /
+ * the C++ classes in include/fov360/<class>.h (SATEncoder / SATDecoder / ImageSampler /
  * OpenCLManager, same names and signatures as the reference) are written against.
  *
  * Conventions (identical to the reference unless stated):
