@@ -71,3 +71,30 @@ def test_product_arm_line():
     assert sv["streams_per_gpu"] == 8 and sv["resident"]["frames_per_s"] > 0
     assert "perf_counter" in sv["resident"]["timing"] and sv["server_lane"]["value"] > 0
     assert cfg["1080p_centre_gaze"]["cpu_reference"]["value"] > 0
+
+
+def test_committed_traffic_capture_matches_the_kernel_sources():
+    """`roofline.traffic` comes from an `ncu --set full` capture under profiles/; every entry carries
+    the hash of the kernel's source files at capture time.  This fails when a kernel was edited
+    without a new capture (tools/refresh_profiles.sh), instead of the number going silently stale."""
+    import sys
+
+    sys.path.insert(0, ROOT)
+    import bench
+
+    for kernel in ("sat_onepass", "sat_sample_rect", "sat_interpolate_rect"):
+        t = bench.measured_traffic("8k", 16, kernel)
+        assert t["traffic"] and t["traffic_state"] == "current", (kernel, t)
+    t = bench.measured_traffic("8k", 16, "no_such_kernel")
+    assert t["traffic"] is None and t["traffic_state"] == "no capture"
+
+
+def test_numa_binding_is_a_no_op_without_topology():
+    import sys
+
+    sys.path.insert(0, ROOT)
+    import bench
+
+    before = os.sched_getaffinity(0)
+    info = bench.bind_to_gpu_numa(0)  # no NVML / no GPU here: must not raise, must not bind
+    assert info["bound"] is False and os.sched_getaffinity(0) == before
