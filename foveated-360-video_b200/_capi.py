@@ -25,6 +25,8 @@ PROTOTYPES = {
     "fov_ctx_stream": (_vp, [_vp]),
     "fov_sync": (_i, [_vp]),
     "fov_ctx_launch_count": (C.c_uint64, [_vp]),
+    "fov_ctx_set_option": (C.c_int, [_vp, C.c_int, C.c_int]),
+    "fov_ctx_get_option": (C.c_int, [_vp, C.c_int, C.POINTER(C.c_int)]),
     "fov_profile_enable": (_i, [_vp, _i]),
     "fov_profile_reset": (_i, [_vp]),
     "fov_profile_count": (_i, [_vp]),

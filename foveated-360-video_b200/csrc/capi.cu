@@ -19,7 +19,10 @@ struct fov_ctx {
   uint64_t launches = 0;
   Profiler prof;
   // per-kernel event timing is off while a graph is being captured (the events would be replayed)
-  LaunchCtx lc() { return LaunchCtx{stream, sm_count, device, capturing ? nullptr : &prof, &launches}; }
+  bool reduced_pad_zero = false;  // fov_ctx_set_option(FOV_OPT_REDUCED_PAD_ZERO)
+  LaunchCtx lc() {
+    return LaunchCtx{stream, sm_count, device, capturing ? nullptr : &prof, &launches, reduced_pad_zero};
+  }
   SatScratch sat_scratch;
   bool sat_scratch_dirty = true;  // holds bytes that are not carry units of an earlier epoch
   uint32_t sat_epoch = 0;         // one-pass launches since the last clear (the epoch itself is
@@ -340,6 +343,22 @@ const char *fov_last_error_string(const fov_ctx *ctx) {
 int fov_ctx_device(const fov_ctx *ctx) { return ctx ? ctx->device : -1; }
 void *fov_ctx_stream(const fov_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
 uint64_t fov_ctx_launch_count(const fov_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+int fov_ctx_set_option(fov_ctx *ctx, int option, int value) {
+  FOV_REQUIRE_CTX(ctx);
+  if (ctx->capturing)
+    return fail(ctx, FOV_ERR_INVALID, "fov_ctx_set_option: set options before fov_graph_begin_capture");
+  if (option != FOV_OPT_REDUCED_PAD_ZERO)
+    return fail(ctx, FOV_ERR_INVALID, "fov_ctx_set_option: unknown option " + std::to_string(option));
+  ctx->reduced_pad_zero = value != 0;
+  return FOV_OK;
+}
+
+int fov_ctx_get_option(const fov_ctx *ctx, int option, int *value) {
+  if (!ctx || !value || option != FOV_OPT_REDUCED_PAD_ZERO) return FOV_ERR_INVALID;
+  *value = ctx->reduced_pad_zero ? 1 : 0;
+  return FOV_OK;
+}
 
 int fov_sync(fov_ctx *ctx) {
   FOV_REQUIRE_CTX(ctx);

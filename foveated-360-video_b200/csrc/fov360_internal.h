@@ -105,6 +105,7 @@ struct LaunchCtx {
   int device = 0;
   Profiler *prof = nullptr;
   uint64_t *launches = nullptr;
+  bool reduced_pad_zero = false;  // FOV_OPT_REDUCED_PAD_ZERO: sample_rect may write whole pixels
 };
 
 // RAII bracket around ONE kernel launch: counts it and, when profiling, times it.

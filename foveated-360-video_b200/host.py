@@ -89,6 +89,17 @@ class OpenCLManager:
     def launch_count(self) -> int:
         return int(self.lib.fov_ctx_launch_count(self.ctx))
 
+    OPT_REDUCED_PAD_ZERO = 1
+
+    def set_option(self, option: int, value: bool) -> None:
+        """fov_ctx_set_option: promises the reference interface cannot state (include/fov360.h)."""
+        self._check(self.lib.fov_ctx_set_option(self.ctx, int(option), int(bool(value))))
+
+    def get_option(self, option: int) -> bool:
+        v = C.c_int(0)
+        self._check(self.lib.fov_ctx_get_option(self.ctx, int(option), C.byref(v)))
+        return bool(v.value)
+
     def profile(self, on: bool) -> None:
         self._check(self.lib.fov_profile_enable(self.ctx, int(on)))
 

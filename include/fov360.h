@@ -63,6 +63,20 @@ int fov_sync(fov_ctx *ctx);
 /* Number of kernels launched through this context so far (bench accounting). */
 uint64_t fov_ctx_launch_count(const fov_ctx *ctx);
 
+/* Context options: promises a caller may make that the reference's interface has no way to state.
+ * All default to 0, i.e. exactly the reference's behaviour for arbitrary buffer contents.
+ *
+ * FOV_OPT_REDUCED_PAD_ZERO: byte 3 of every pixel of the reduced buffers handed to
+ *   SampleFrameRectGPU (all fov_sat_sample_rect* / encode_sample* / foveate* entry points) is 0 and
+ *   may be (re)written as 0 - e.g. the buffer was cleared once when it was allocated, as a buffer
+ *   that goes on to a video encoder normally is.  sample_rect then writes each sampled pixel as one
+ *   32-bit word (r, g, b, 0) instead of the reference's 3-byte .xyz store
+ *   (sat_decoder_sample_rect_kernel.cl:240).  Under the promise the buffer contents are identical;
+ *   pixels whose box misses the frame are still left untouched.  Kernel time -7 % at 8K x 16. */
+enum { FOV_OPT_REDUCED_PAD_ZERO = 1 };
+int fov_ctx_set_option(fov_ctx *ctx, int option, int value);
+int fov_ctx_get_option(const fov_ctx *ctx, int option, int *value);
+
 /* Per-kernel device timing (the role of CL_QUEUE_PROFILING_ENABLE + clGetEventProfilingInfo;
  * the reference creates its queue without it, opencl_manager.cc:55).  While enabled, every kernel
  * launched through the context is bracketed by CUDA events on the context's stream; totals are

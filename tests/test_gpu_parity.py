@@ -623,6 +623,59 @@ def test_encode_sample_batched_equals_separate_calls(dev, fov, oracle):
         assert np.array_equal(got_red[f], want), f
 
 
+def test_reduced_pad_zero_option(dev, fov, oracle):
+    """FOV_OPT_REDUCED_PAD_ZERO (include/fov360.h): the caller promises byte 3 of the reduced pixels
+    is 0, sample_rect writes whole 32-bit pixels.  Under the promise every buffer is bit-identical
+    to the oracle's (single calls, the fused batch, host and device gaze, gazes whose boxes miss
+    the frame); without it bytes 0..2 still are, byte 3 of a SAMPLED pixel reads 0 and untouched
+    pixels keep all four bytes."""
+    W, H, n = 640, 360, 4
+    ow, oh = fov.reduced_dim(W), fov.reduced_dim(H)
+    frames = np.stack([O.lcg_frame(W, H, 70 + f) for f in range(n)])
+    gaze = np.asarray([(0.5, 0.5), (0.0, 1.0), (0.97, 0.03), (0.25, 0.6)], np.float32)
+    assert not dev.m.get_option(dev.m.OPT_REDUCED_PAD_ZERO)
+    dev.m.set_option(dev.m.OPT_REDUCED_PAD_ZERO, True)
+    try:
+        assert dev.m.get_option(dev.m.OPT_REDUCED_PAD_ZERO)
+        sats = [oracle.sat_encode(frames[f]) for f in range(n)]
+        for f in range(n):
+            cx, cy = float(gaze[f, 0]), float(gaze[f, 1])
+            _, sat_buf = dev.sat(frames[f])
+            got, _ = dev.sample(sat_buf, W, H, ow, oh, cx, cy, prefill=0)
+            assert np.array_equal(got, oracle.sat_sample_rect(sats[f], ow, oh, cx, cy,
+                                                              out=np.zeros((oh, ow, 4), np.uint8))), f
+            # promise broken on purpose: what the option does to a buffer that is not cleared
+            got, _ = dev.sample(sat_buf, W, H, ow, oh, cx, cy, prefill=0xAB)
+            lo = oracle.sat_sample_rect(sats[f], ow, oh, cx, cy, out=np.zeros((oh, ow, 4), np.uint8))
+            hi = oracle.sat_sample_rect(sats[f], ow, oh, cx, cy, out=np.full((oh, ow, 4), 255, np.uint8))
+            written = (lo[..., :3] == hi[..., :3]).all(axis=-1)
+            want = ab(oh, ow)
+            want[written] = lo[written]
+            assert np.array_equal(got, want), f
+        src = dev.m.upload(frames)
+        sat = dev.m.Buffer(n * 12 * W * H)
+        for dev_gaze in (False, True):
+            red = dev.m.upload(np.zeros((n, oh, ow, 4), np.uint8))
+            full = dev.m.Buffer(n * 4 * W * H)
+            args = (dev.m, n, full, 4 * W * H, red, 4 * ow * oh, sat, 12 * W * H, src, 4 * W * H, W, H,
+                    4 * W, ow, oh)
+            if dev_gaze:
+                fov.FoveateFramesDeviceGazeGPU(*args, dev.m.upload(gaze))
+            else:
+                fov.FoveateFramesGPU(*args, gaze)
+            got_red = dev.m.copy_to_host(np.empty((n, oh, ow, 4), np.uint8), red)
+            got_full = dev.m.copy_to_host(np.empty((n, H, W, 4), np.uint8), full)
+            for f in range(n):
+                cx, cy = float(gaze[f, 0]), float(gaze[f, 1])
+                want = oracle.sat_sample_rect(sats[f], ow, oh, cx, cy, out=np.zeros((oh, ow, 4), np.uint8))
+                assert np.array_equal(got_red[f], want), (dev_gaze, f)
+                assert np.array_equal(got_full[f], oracle.sat_interpolate_rect(want, W, H, cx, cy)), f
+    finally:
+        dev.m.set_option(dev.m.OPT_REDUCED_PAD_ZERO, False)
+    with pytest.raises(fov.FovError):
+        dev.m.set_option(99, True)
+
+
 def test_launch_chain_keeps_queue_order(dev, fov, oracle):
     """The encode / sample / interpolate kernels are launched with programmatic dependent launch
     (their CTAs may become resident while the predecessor drains).  The in-order semantics of the

@@ -18,6 +18,8 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--workload", default="8k")
 ap.add_argument("--batch", type=int, default=2)
 ap.add_argument("--steps", type=int, default=2)
+ap.add_argument("--pad-zero", action="store_true",
+                help="FOV_OPT_REDUCED_PAD_ZERO: sample_rect writes whole pixels (buffer cleared below)")
 args = ap.parse_args()
 
 fov = importlib.import_module("foveated-360-video_b200")
@@ -30,6 +32,7 @@ fb, sb, rb = 4 * W * H, 12 * W * H, 4 * ow * oh
 frames = np.stack([bench.synth_frame(W, H, f) for f in range(B)])
 src, sat, red, full = m.upload(frames), m.Buffer(B * sb), m.Buffer(B * rb), m.Buffer(B * fb)
 m.memset(red, 0, B * rb)
+m.set_option(m.OPT_REDUCED_PAD_ZERO, args.pad_zero)
 gaze = bench.gaze_trace(args.steps, B, seed=1)
 for i in range(args.steps):
     fov.FoveateFramesGPU(m, B, full, fb, red, rb, sat, sb, src, fb, W, H, 4 * W, ow, oh, gaze[i])
