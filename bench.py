@@ -1028,7 +1028,8 @@ def main():
     ap.add_argument("--batch", type=int, default=16,
                     help="frames per step per GPU (SURVEY 8(d): cfg3 is a batch of 16 frames)")
     ap.add_argument("--e2e-depth", type=int, default=6)
-    ap.add_argument("--serve-frames", type=int, default=120)
+    ap.add_argument("--serve-frames", type=int, default=300,
+                    help="frames per stream of the serving config (SURVEY 8(d) cfg5: 300)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-configs", action="store_true", help="headline only")
     ap.add_argument("--no-server-lane", action="store_true")
