@@ -50,6 +50,7 @@ constexpr int kGatherRows = FOV360_GATHER_ROWS;  // reduced rows per thread: tha
 __global__ void __launch_bounds__(256) img_sample_rect_kernel(const GatherArgs a,
                                                               const int16_t *__restrict__ xd,
                                                               const int16_t *__restrict__ yd) {
+  pdl_trigger();
   const int i = blockIdx.x * 32 + threadIdx.x;
   const int j0 = (blockIdx.y * 8 + threadIdx.y) * kGatherRows;
   if (i >= a.ow || j0 >= a.oh) return;
@@ -60,6 +61,7 @@ __global__ void __launch_bounds__(256) img_sample_rect_kernel(const GatherArgs a
   else if (x < 0)
     x += a.W;
   if (x < 0 || x >= a.W) return;  // :35: the column keeps its contents
+  pdl_wait();  // tables above; the frame and the target buffer below
   const uint8_t *scol = a.src + (size_t)x * a.sbpp;
   uint8_t *ocol = a.out + (size_t)i * a.obpp;
   if (a.word_ok) {
@@ -104,6 +106,7 @@ __device__ __forceinline__ int mod_width(int v, int w, float rcp_w) {
 __global__ void __launch_bounds__(256) img_sample_logpolar_kernel(
     const GatherArgs a, const float *__restrict__ radius, const float *__restrict__ cs,
     const float *__restrict__ sn) {
+  pdl_trigger();
   const int i = blockIdx.x * 32 + threadIdx.x;
   const int j0 = (blockIdx.y * 8 + threadIdx.y) * kGatherRows;
   if (i >= a.ow || j0 >= a.oh) return;
@@ -126,6 +129,7 @@ __global__ void __launch_bounds__(256) img_sample_logpolar_kernel(
     if (on[k]) FOV_CHECK((size_t)y * a.src_linesize + (size_t)x * a.sbpp + (a.word_ok ? 3 : 2), (size_t)a.H * a.src_linesize, 113);
     sp[k] = a.src + (size_t)y * a.src_linesize + (size_t)max(x, 0) * a.sbpp;
   }
+  pdl_wait();  // tables above; the frame and the target buffer below
   if (a.word_ok) {
     uint32_t v[kGatherRows];
 #pragma unroll
@@ -237,6 +241,7 @@ __device__ __forceinline__ bool logpolar_hits(const LpInterpArgs &a, int i, int 
 #endif
 __global__ void __launch_bounds__(kLpThreads, FOV360_LP_MIN_CTAS) img_interpolate_logpolar_kernel(const LpInterpArgs a) {
   __shared__ LpRow srows[kLpMaxRows];
+  pdl_trigger();
   const int W = a.W, H = a.H, ow = a.ow, oh = a.oh;
   const int xx = blockIdx.x * kLpThreads + threadIdx.x;
   const int y0 = blockIdx.y * a.rows;
@@ -274,6 +279,7 @@ __global__ void __launch_bounds__(kLpThreads, FOV360_LP_MIN_CTAS) img_interpolat
   const uint32_t magic = a.magic;
   const float ow_top = (float)(ow - 1);
 
+  pdl_wait();  // row and column set-up above; the reduced buffer and the target below
   for (int r0 = 0; r0 < nrows; r0 += 2, op += 2 * (size_t)W) {
     float i_f[2], j_f[2], tt[2], aa[2];
     bool swp[2], neg[2], centre[2];
@@ -401,6 +407,8 @@ __global__ void __launch_bounds__(kLpThreads, FOV360_LP_MIN_CTAS) img_interpolat
 __global__ void __launch_bounds__(256) img_logpolar_blur_kernel(uint32_t *__restrict__ out, int ow,
                                                                 int oh,
                                                                 const uint32_t *__restrict__ src) {
+  pdl_trigger();
+  pdl_wait();
   const int i = blockIdx.x * 32 + threadIdx.x;
   const int j = blockIdx.y * 8 + threadIdx.y;
   if (i >= ow || j >= oh) return;
@@ -464,6 +472,8 @@ __device__ __forceinline__ float half_hi_to_float(uint32_t v) {
 
 __global__ void __launch_bounds__(32 * kBlurWarps, 6) img_logpolar_blur4_kernel(
     uint4 *__restrict__ out, int ow, int oh, const uint32_t *__restrict__ src) {
+  pdl_trigger();
+  pdl_wait();  // nothing to prepare: every value comes from the predecessor's buffer
   const int lane = threadIdx.x, warp = threadIdx.y;
   const int ow4 = ow >> 2;
   const int g = blockIdx.x * 32 + lane;
@@ -581,9 +591,8 @@ cudaError_t launch_img_sample_rect(const LaunchCtx &lc, uint8_t *out, int ow, in
                                    const int16_t *xd, const int16_t *yd, float cx, float cy) {
   const dim3 grid((ow + 31) / 32, (oh + 8 * kGatherRows - 1) / (8 * kGatherRows)), block(32, 8);
   KernelScope ks(lc, "img_sample_rect");
-  img_sample_rect_kernel<<<grid, block, 0, lc.stream>>>(
-      make_gather(out, ow, oh, out_linesize, src, W, H, src_linesize, cx, cy), xd, yd);
-  return cudaGetLastError();
+  return launch_chained(img_sample_rect_kernel, grid, block, 0, lc.stream,
+                        make_gather(out, ow, oh, out_linesize, src, W, H, src_linesize, cx, cy), xd, yd);
 }
 
 cudaError_t launch_img_sample_logpolar(const LaunchCtx &lc, uint8_t *out, int ow, int oh,
@@ -592,9 +601,9 @@ cudaError_t launch_img_sample_logpolar(const LaunchCtx &lc, uint8_t *out, int ow
                                        const float *sn, float cx, float cy) {
   const dim3 grid((ow + 31) / 32, (oh + 8 * kGatherRows - 1) / (8 * kGatherRows)), block(32, 8);
   KernelScope ks(lc, "img_sample_logpolar");
-  img_sample_logpolar_kernel<<<grid, block, 0, lc.stream>>>(
-      make_gather(out, ow, oh, out_linesize, src, W, H, src_linesize, cx, cy), radius, cs, sn);
-  return cudaGetLastError();
+  return launch_chained(img_sample_logpolar_kernel, grid, block, 0, lc.stream,
+                        make_gather(out, ow, oh, out_linesize, src, W, H, src_linesize, cx, cy), radius,
+                        cs, sn);
 }
 
 cudaError_t launch_img_interpolate_logpolar(const LaunchCtx &lc, uint8_t *out, int W, int H,
@@ -627,8 +636,7 @@ cudaError_t launch_img_interpolate_logpolar(const LaunchCtx &lc, uint8_t *out, i
   a.rows = ctas32 >= (size_t)4 * lc.sm_count ? 32 : 16;
   const dim3 grid_dim((W + kLpThreads - 1) / kLpThreads, (H + a.rows - 1) / a.rows);
   KernelScope ks(lc, "img_interpolate_logpolar");
-  img_interpolate_logpolar_kernel<<<grid_dim, kLpThreads, 0, lc.stream>>>(a);
-  return cudaGetLastError();
+  return launch_chained(img_interpolate_logpolar_kernel, grid_dim, dim3(kLpThreads), 0, lc.stream, a);
 }
 
 cudaError_t launch_img_logpolar_blur(const LaunchCtx &lc, uint8_t *out, int ow, int oh,
@@ -637,14 +645,15 @@ cudaError_t launch_img_logpolar_blur(const LaunchCtx &lc, uint8_t *out, int ow, 
   if ((ow & 3) == 0 && ((uintptr_t)out & 15) == 0 && ((uintptr_t)src & 15) == 0) {
     const dim3 grid((ow / 4 + 31) / 32, (oh + kBlurWarps * kBlurRows - 1) / (kBlurWarps * kBlurRows)),
         block(32, kBlurWarps);
-    img_logpolar_blur4_kernel<<<grid, block, 0, lc.stream>>>(
-        reinterpret_cast<uint4 *>(out), ow, oh, reinterpret_cast<const uint32_t *>(src));
+    return launch_chained(img_logpolar_blur4_kernel, grid, block, 0, lc.stream,
+                          reinterpret_cast<uint4 *>(out), ow, oh,
+                          reinterpret_cast<const uint32_t *>(src));
   } else {
     const dim3 grid((ow + 31) / 32, (oh + 7) / 8), block(32, 8);
-    img_logpolar_blur_kernel<<<grid, block, 0, lc.stream>>>(
-        reinterpret_cast<uint32_t *>(out), ow, oh, reinterpret_cast<const uint32_t *>(src));
+    return launch_chained(img_logpolar_blur_kernel, grid, block, 0, lc.stream,
+                          reinterpret_cast<uint32_t *>(out), ow, oh,
+                          reinterpret_cast<const uint32_t *>(src));
   }
-  return cudaGetLastError();
 }
 
 cudaError_t launch_img_logpolar_grid_expand(const LaunchCtx &lc, int16_t *grid, int ow, int oh,

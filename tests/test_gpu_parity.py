@@ -602,6 +602,47 @@ def test_image_sampler_three_byte_pixels(dev, oracle):
                                   oracle.img_sample_logpolar(frame, ow, oh, cx, cy, out=pre.copy()))
 
 
+def test_image_sampler_chain_keeps_queue_order(dev, fov):
+    """The ImageSampler kernels are chained with programmatic dependent launch too.  A sequence in
+    which every call consumes what the previous one produced, through the SAME buffers (the
+    un-warped frame of pass k is the source of pass k + 1, rect and log-polar sampling alternate)
+    and with nothing waiting in between, must leave exactly the bytes the same sequence leaves when
+    the host waits after every call (no two kernels ever overlap then)."""
+    W, H = 640, 360
+    ow, oh = fov.reduced_dim(W), fov.reduced_dim(H)
+    frame = O.smooth_frame(W, H, seed=23)
+    gazes = [(0.5, 0.5), (0.31, 0.77), (0.98, 0.05), (0.02, 0.6), (0.66, 0.33), (1.0, 1.0)]
+
+    def run(wait):
+        img = dev.m.upload(frame)
+        lp = dev.m.upload(np.zeros((oh, ow, 4), np.uint8))
+        bl = dev.m.upload(np.zeros((oh, ow, 4), np.uint8))
+        rect = dev.m.upload(np.zeros((oh, ow, 4), np.uint8))
+
+        def sync():
+            if wait:
+                dev.m.Finish()
+
+        for cx, cy in gazes:
+            dev.img.SampleFrameRectGPU(rect, ow, oh, 4 * ow, img, W, H, 4 * W, cx, cy)
+            sync()
+            dev.img.SampleFrameLogPolarGPU(lp, ow, oh, 4 * ow, img, W, H, 4 * W, cx, cy)
+            sync()
+            dev.img.ApplyLogPolarGaussianBlur(bl, ow, oh, 4 * ow, lp)
+            sync()
+            dev.img.InterpolateFrameLogPolarGPU(img, W, H, 4 * W, bl, ow, oh, 4 * ow, cx, cy)
+            sync()
+        return [dev.m.copy_to_host(np.empty(shape, np.uint8), b)
+                for b, shape in ((img, (H, W, 4)), (lp, (oh, ow, 4)), (bl, (oh, ow, 4)),
+                                 (rect, (oh, ow, 4)))]
+
+    want = run(wait=True)
+    for attempt in range(3):
+        got = run(wait=False)
+        for g, w in zip(got, want):
+            assert np.array_equal(g, w), attempt
+
+
 def test_encode_sample_batched_equals_separate_calls(dev, fov, oracle):
     """fov_sat_encode_sample_batched (the server's two stages, video_server.cc:300-338) against the
     single-frame calls and the oracle: SATs and reduced buffers bit-identical, per-frame gaze."""
