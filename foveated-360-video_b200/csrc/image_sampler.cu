@@ -8,6 +8,8 @@
 // replaced by their separable 1-D factors (luts.cc); the grid value is re-formed in
 // registers, which removes a 4 B/pixel table read from both samplers.
 #include "bounds_check.cuh"
+#include <cstdlib>
+
 #include "fov360_internal.h"
 #include "pixel_math.cuh"
 
@@ -630,10 +632,21 @@ cudaError_t launch_img_interpolate_logpolar(const LaunchCtx &lc, uint8_t *out, i
   a.turns = (float)turns;
   a.zone = logpolar_round_zone(oh);
   a.magic = 0x4B000000u;
-  // rows per CTA by the amount of work: fewer, taller tiles amortise the per-column set-up; a small
-  // frame needs enough CTAs to fill the GPU
-  const size_t ctas32 = (size_t)((W + kLpThreads - 1) / kLpThreads) * ((H + 31) / 32);
-  a.rows = ctas32 >= (size_t)4 * lc.sm_count ? 32 : 16;
+  // Rows per CTA, measured on a B200 (tools/sweep_tile_rows.sh, profiles/r02_tile_rows.txt): rows
+  // near the gaze cost more than the others (both rounding candidates tested, exact re-evaluation),
+  // so short tiles balance better than the per-column set-up they repeat costs - 1080p 0.0219 ms
+  // with 8 rows against 0.0244 with 16, 4K 0.0535 (10) against 0.0603 (32), 8K 0.1807 (20) against
+  // 0.1833 (32).  A model that sized the tiles to fill whole waves of CTAs (one 4K frame = exactly
+  // one wave of 50-row tiles) was 7 % slower than 32 rows.  FOV360_LP_ROWS overrides for sweeps.
+  {
+    static const int force = [] {
+      const char *e = getenv("FOV360_LP_ROWS");
+      const int v = e ? atoi(e) : 0;
+      return (v >= 2 && v <= kLpMaxRows) ? v : 0;
+    }();
+    const size_t px = (size_t)W * H;
+    a.rows = force ? force : (px < ((size_t)3 << 20) ? 8 : (px < ((size_t)12 << 20) ? 10 : 20));
+  }
   const dim3 grid_dim((W + kLpThreads - 1) / kLpThreads, (H + a.rows - 1) / a.rows);
   KernelScope ks(lc, "img_interpolate_logpolar");
   return launch_chained(img_interpolate_logpolar_kernel, grid_dim, dim3(kLpThreads), 0, lc.stream, a);
