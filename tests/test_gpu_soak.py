@@ -23,11 +23,12 @@ def test_numpy_sat_wraps_like_the_kernels():
     import numpy as np
 
     tool = load_tool()
-    frame = np.full((300, 70000 // 4, 4), 255, np.uint8)  # 5.25 M pixels of 255: wraps past 2^32? no,
-    sat = tool.numpy_sat(frame)                           # so force it with a tall stack below
-    assert sat.dtype == np.uint32
-    assert int(sat[-1, -1, 0]) == (255 * 300 * (70000 // 4)) % (1 << 32)
-    big = np.full((4400, 4096, 4), 255, np.uint8)  # 255 * 18 M = 4.6e9 > 2^32
+    small = np.full((300, 1000, 4), 255, np.uint8)
+    sat = tool.numpy_sat(small)
+    assert sat.dtype == np.uint32 and sat.shape == (300, 1000, 3)
+    assert int(sat[-1, -1, 0]) == 255 * 300 * 1000
+    assert int(sat[9, 4, 1]) == 255 * 10 * 5
+    big = np.full((4400, 4096, 4), 255, np.uint8)  # 255 * 18 M pixels = 4.6e9 > 2^32: wraps
     assert int(tool.numpy_sat(big)[-1, -1, 2]) == (255 * 4400 * 4096) % (1 << 32)
 
 
