@@ -115,7 +115,10 @@ __global__ void __launch_bounds__(32 * kSampleWarps, FOV360_SAMPLE_MIN_CTAS)
   const int jb = blockIdx.y * kSampleWarps * kSampleRows;
   const int f = blockIdx.z;
   const int W = a.W, H = a.H, ow = a.ow, oh = a.oh;
-  // kDevGaze is a template parameter: the run-time form of this choice cost the by-value path 1 %
+  // kDevGaze is a template parameter: the run-time form of this choice cost the by-value path 1 %.
+  // A device-side gaze array may itself have been produced on this stream (a copy, or the caller's
+  // own kernel), so those instantiations wait before they read it and overlap the launch only.
+  if (kDevGaze) pdl_wait();
   const int cxp = gaze_px(kDevGaze ? __ldg(g.dev + 2 * f) : g.xy[2 * f], W);
   const int cyp = gaze_px(kDevGaze ? __ldg(g.dev + 2 * f + 1) : g.xy[2 * f + 1], H);
   const uint32_t row_words = (uint32_t)W * 3u;
@@ -417,7 +420,10 @@ __global__ void __launch_bounds__(32 * kInterpWarps, FOV360_INTERP_MIN_CTAS)
   const int y0 = (blockIdx.y * kInterpWarps + warp) * kInterpRows;
   const int f = blockIdx.z;
   const int W = a.W, H = a.H, ow = a.ow, oh = a.oh;
-  // kDevGaze is a template parameter: the run-time form of this choice cost the by-value path 1 %
+  // kDevGaze is a template parameter: the run-time form of this choice cost the by-value path 1 %.
+  // A device-side gaze array may itself have been produced on this stream (a copy, or the caller's
+  // own kernel), so those instantiations wait before they read it and overlap the launch only.
+  if (kDevGaze) pdl_wait();
   const int cxp = gaze_px(kDevGaze ? __ldg(g.dev + 2 * f) : g.xy[2 * f], W);
   const int cyp = gaze_px(kDevGaze ? __ldg(g.dev + 2 * f + 1) : g.xy[2 * f + 1], H);
   const uint32_t *red = reinterpret_cast<const uint32_t *>(a.red + (size_t)f * a.red_stride);

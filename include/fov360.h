@@ -185,7 +185,9 @@ int fov_sat_encode_sample_batched(fov_ctx *ctx, int n, uint8_t *reduced, size_t 
 /* The two sequences above with the gaze array in DEVICE memory (2n floats, frame f at 2f, 2f+1):
  * nothing in the launches changes from frame to frame - the gaze is read by the kernels, the SAT
  * build keeps its launch epoch on the device - so a sequence can be captured once as a CUDA graph
- * and replayed (the 3-stage pipeline as a single submission). */
+ * and replayed (the 3-stage pipeline as a single submission).  The array
+ * is read in stream order: whatever wrote it earlier on the context's stream (fov_memcpy_h2d_async,
+ * or a kernel of the caller's on fov_ctx_stream) is complete before the kernels read it. */
 int fov_sat_encode_sample_batched_dev(fov_ctx *ctx, int n, uint8_t *reduced, size_t red_stride,
                                       uint32_t *sat, size_t sat_stride, const uint8_t *src,
                                       size_t src_stride, int src_width, int src_height,
