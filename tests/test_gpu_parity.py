@@ -815,6 +815,43 @@ def test_captured_graph_replays_with_new_gaze(dev, fov, oracle):
     assert np.array_equal(m.copy_to_host(np.empty((n, H, W, 3), np.uint32), sat), np.stack(want_sat))
 
 
+def test_device_gaze_written_by_a_kernel_on_the_same_stream(dev, fov, oracle):
+    """The *_dev entry points read the gaze in stream order (include/fov360.h): here a kernel of the
+    caller's (a torch element-wise op on the context's stream) produces the gaze array immediately
+    before every call, nothing waits in between, and every call must have used ITS gaze - the
+    chained kernels may not read the array while their predecessors are still running."""
+    import torch
+
+    m = dev.m
+    W, H, n, rounds = 640, 360, 2, 10
+    ow, oh = fov.reduced_dim(W), fov.reduced_dim(H)
+    frames = np.stack([O.lcg_frame(W, H, 90 + f) for f in range(n)])
+    src = m.upload(frames)
+    sat, full = m.Buffer(n * 12 * W * H), m.Buffer(n * 4 * W * H)
+    reds = [m.upload(np.zeros((n, oh, ow, 4), np.uint8)) for _ in range(rounds)]
+    rng = np.random.default_rng(5)
+    gazes = rng.random((rounds, n, 2)).astype(np.float32)
+    stream = torch.cuda.ExternalStream(m.stream)
+    with torch.cuda.stream(stream):
+        table = torch.from_numpy(gazes).cuda()          # all gazes, resident
+        gaze_t = torch.zeros(n, 2, dtype=torch.float32, device="cuda")
+    m.Finish()
+    torch.cuda.synchronize()
+    for k in range(rounds):  # nothing waits inside this loop
+        with torch.cuda.stream(stream):
+            torch.add(table[k], 0.0, out=gaze_t)      # a kernel writes the gaze of this call
+        fov.FoveateFramesDeviceGazeGPU(m, n, full, 4 * W * H, reds[k], 4 * ow * oh, sat, 12 * W * H,
+                                       src, 4 * W * H, W, H, 4 * W, ow, oh, gaze_t.data_ptr())
+    m.Finish()
+    want_sat = [oracle.sat_encode(frames[f]) for f in range(n)]
+    for k in range(rounds):
+        got = m.copy_to_host(np.empty((n, oh, ow, 4), np.uint8), reds[k])
+        for f in range(n):
+            cx, cy = float(gazes[k, f, 0]), float(gazes[k, f, 1])
+            want = oracle.sat_sample_rect(want_sat[f], ow, oh, cx, cy, out=np.zeros((oh, ow, 4), np.uint8))
+            assert np.array_equal(got[f], want), (k, f)
+
+
 def test_device_gaze_batch_larger_than_one_launch(dev, fov, oracle):
     """More frames than one launch carries gaze slots for (64): the device gaze pointer advances
     with the chunk, like the host array does."""
